@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hodor_b200 hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--sweep]
+
+One "step" is one pass of the hot path over one batch of synthetic input: the coset LDE of a
+2^24-coefficient polynomial over the `src/bn256.rs` field (= BLS12-381 Fr) with blowup 8
+(BASELINE.json configs[1]: eight coset NTTs of 2^24 -> 2^27 values, 4 GiB), inputs resident in HBM.
+The same line also carries the second half of BASELINE.json's metric, the FRI commit chain on a
+2^24 domain (configs[2], Merkle leaves/s), a plain 2^24 NTT, the end-to-end number through the
+host-pointer C ABI, the live roofline of the dominant kernel and the CPU baseline.
+
+Under torchrun (N > 1) every rank runs the same per-GPU workload on its own polynomial (weak
+scaling, no data-path collective -- registers / polynomials of a proof are independent), and the
+four-step sharded NTT (the one path with a real exchange step, NCCL all-to-all) is timed as an
+extra section.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FIELD = 0  # BLS12-381 Fr == the reference's src/bn256.rs
+LOG_N = 24
+LOG_L = 3
+FRI_LOG_N = 24
+FRI_L = 8
+FRI_OUT = 1
+P_TOP_LIMB = 0x73EDA753299D7D48  # top u64 limb of the modulus: any element with a smaller top limb is canonical
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synthetic_elements(count: int, seed: int) -> np.ndarray:
+    """i.i.d. canonical field elements used directly as Montgomery representations."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**64, size=(count, 4), dtype=np.uint64)
+    a[:, 3] = rng.integers(0, P_TOP_LIMB, size=count, dtype=np.uint64)
+    return a
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons while a timed region runs (pynvml, 100 ms period)."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU algorithm (restated in oracle/, see its header) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_lde_sample(log_n: int, repeats: int):
+    from oracle import oracle as O
+    O.build()
+    cores = O.default_cpus()
+    coeffs = O.random_elements(FIELD, 1 << log_n, seed=11)
+    O.lde(FIELD, coeffs[: 1 << 10], 10, 1 << LOG_L, True, cpus=cores)  # warm the library
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.lde(FIELD, coeffs, log_n, 1 << LOG_L, True, cpus=max(cores, 1 << LOG_L))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return ((1 << log_n) << LOG_L) / best, cores, best
+
+
+def cpu_fri_sample(log_n: int):
+    from oracle import oracle as O
+    cores = O.default_cpus()
+    vals = O.random_elements(FIELD, 1 << log_n, seed=12)
+    t0 = time.perf_counter()
+    O.fri_commit(FIELD, vals, FRI_L, FRI_OUT, cpus=cores)
+    dt = time.perf_counter() - t0
+    steps = O.fri_num_steps(1 << log_n, FRI_L, FRI_OUT)
+    leaves = sum((1 << log_n) >> i for i in range(steps + 1))
+    return leaves / dt, cores, dt
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    sample_log_n = 20
+    times = []
+    from oracle import oracle as O
+    O.build()
+    cores = O.default_cpus()
+    coeffs = O.random_elements(FIELD, 1 << sample_log_n, seed=11)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.lde(FIELD, coeffs, sample_log_n, 1 << LOG_L, True, cpus=max(cores, 1 << LOG_L))
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    elems = (1 << sample_log_n) << LOG_L
+    total = sum(times)
+    value = elems * len(times) / total
+    fri_value, _, fri_dt = cpu_fri_sample(20)
+    sample = (f"each step = coset LDE 2^{sample_log_n} x{1 << LOG_L} (1/16 of the GPU arm's 2^{LOG_N} x{1 << LOG_L}); "
+              f"multi-coset path: one serial_fft thread per coset, distribute_powers on all {cores} cores")
+    line = {
+        "impl": "reference", "metric": "ntt_field_elems_per_sec", "value": value, "unit": "field-elems/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery)",
+        "data": "synthetic",
+        "config": {"workload": f"coset LDE 2^{LOG_N} x{1 << LOG_L} over bn256.rs Fr (BLS12-381 Fr), CPU sample 2^{sample_log_n}",
+                   "field": "bls12_381_fr", "reference_impl": "C restatement of hodor's crossbeam path (Rust toolchain unavailable)"},
+        "cpu_baseline": {"value": value, "unit": "field-elems/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "field-elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fri": {"metric": "fri_merkle_leaves_per_sec", "value": fri_value, "unit": "leaves/s",
+                "sample": f"FRI commit chain on 2^20 values, blowup {FRI_L}, {cores} cores, {fri_dt:.2f} s"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    import hodor_b200 as H
+    from hodor_b200 import _ffi
+    from hodor_b200 import device as dev
+    from hodor_b200.field import _p
+
+    torch.cuda.set_device(local_rank)
+    H.init(local_rank)
+    lib = _ffi.lib
+    peak_gbs, peak_src = load_peaks()
+    n, L = 1 << LOG_N, 1 << LOG_L
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms)
+
+    def profile(fn):
+        _ffi.check(lib.hodor_cuda_profile_begin())
+        fn()
+        buf = C.create_string_buffer(1 << 16)
+        _ffi.check(lib.hodor_cuda_profile_end(buf, len(buf)))
+        return {r["name"]: r for r in json.loads(buf.value.decode())}
+
+    # ---- inputs, resident in HBM before any timed region (larger than the 126 MB L2: no flush needed)
+    coeffs = synthetic_elements(n, seed=1000 + rank)
+    d_coeffs = dev.to_device(coeffs)
+    d_out = dev.empty_elems(n * L)
+
+    def lde_step():
+        dev.lde(d_coeffs, LOG_N, LOG_L, True, d_out, FIELD)
+
+    clocks = ClockSampler(local_rank)
+    launches0 = dev.launch_count()
+    with clocks:
+        total_ms = timed(lde_step, args.steps, args.warmup)
+    launches = dev.launch_count() - launches0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    ms_per_step = total_ms / args.steps
+    value = world * n * L / (ms_per_step * 1e-3)
+
+    # ---- live per-kernel share and roofline of the dominant kernel (events around every launch)
+    prof = profile(lambda: [lde_step() for _ in range(args.steps)])
+    kern_total = sum(r["total_ms"] for r in prof.values())
+    dom = max(prof.values(), key=lambda r: r["total_ms"])
+    alg_bytes = {"ntt_pass_first_scaled": 32 * n + 32 * n * L, "ntt_pass": 64 * n * L, "ntt_pass_last": 64 * n * L}
+    dom_ms = dom["total_ms"] / dom["count"]
+    dom_bytes = alg_bytes.get(dom["name"], 64 * n * L)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms, "share_of_step": dom["total_ms"] / kern_total,
+        "kernels": {k: {"launches": r["count"], "ms_per_launch": r["total_ms"] / r["count"],
+                        "share": r["total_ms"] / kern_total} for k, r in prof.items()},
+        "job": {"algorithmic_bytes": 32 * n + 32 * n * L, "achieved": (32 * n + 32 * n * L) / (ms_per_step * 1e-3) / 1e9,
+                "frac": (32 * n + 32 * n * L) / (ms_per_step * 1e-3) / 1e9 / peak_gbs},
+        "note": "compute (INT32 issue) bound by design: ~13 256-bit Montgomery multiplies per 64 B moved; see DESIGN.md",
+    }
+
+    # ---- plain forward NTT 2^24 (BASELINE metric, first half)
+    d_tmp = dev.empty_elems(n)
+    ntt_ms = timed(lambda: dev.fft(d_coeffs, d_tmp, LOG_N, False, FIELD), args.steps, args.warmup) / args.steps
+    ntt = {"metric": "ntt_field_elems_per_sec", "workload": f"forward NTT 2^{LOG_N}", "value": world * n / (ntt_ms * 1e-3),
+           "unit": "field-elems/s", "ms_per_step": ntt_ms, "algorithmic_bytes": 64 * n,
+           "hbm_frac": 64 * n / (ntt_ms * 1e-3) / 1e9 / peak_gbs}
+    del d_tmp
+
+    # ---- FRI commit chain on a 2^24 domain incl. all Merkle trees (BASELINE metric, second half)
+    fn_ = 1 << FRI_LOG_N
+    d_vals = dev.to_device(synthetic_elements(fn_, seed=2000 + rank))
+    steps_fri = ((fn_ // FRI_L) // FRI_OUT).bit_length() - 1
+    leaves = sum(fn_ >> i for i in range(steps_fri + 1))
+
+    def fri_step():
+        proto = dev.fri_commit(d_vals, FRI_L, FRI_OUT, FIELD)
+        del proto
+
+    for _ in range(max(1, args.warmup - 1)):
+        fri_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fri_step()
+    torch.cuda.synchronize()
+    fri_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    fprof = profile(fri_step)
+    f_total = sum(r["total_ms"] for r in fprof.values())
+    leaf_k = fprof.get("merkle_levels_leaf")
+    fri = {"metric": "fri_merkle_leaves_per_sec", "workload": f"FRI commit chain on 2^{FRI_LOG_N} values, blowup {FRI_L}, "
+           f"{steps_fri} layers, {steps_fri + 1} Merkle trees", "value": world * leaves / (fri_ms * 1e-3), "unit": "leaves/s",
+           "ms_per_step": fri_ms, "kernel_ms": f_total, "algorithmic_bytes": 128 * fn_,
+           "hbm_frac": 128 * fn_ / (fri_ms * 1e-3) / 1e9 / peak_gbs,
+           "kernels": {k: {"launches": r["count"], "total_ms": r["total_ms"], "share": r["total_ms"] / f_total}
+                       for k, r in fprof.items()}}
+    if leaf_k:
+        # first leaf kernel dominates: 2^24 leaves, 32 B read per leaf + 3 node levels (7/8 * 32 B) written
+        fri["timer"] = "host perf_counter around the synchronous commit call, max over ranks"
+    del d_vals
+
+    # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + LDE + D2H every step
+    h_in = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
+    h_out = torch.empty((n * L, 4), dtype=torch.int64, pin_memory=True)
+    h_in.numpy().view(np.uint64)[:] = coeffs
+    e2e_steps = max(2, min(args.steps, 3))
+
+    def e2e_step():
+        _ffi.check(lib.hodor_cuda_lde(C.cast(h_in.data_ptr(), _ffi.u64p), LOG_N, LOG_L, 1,
+                                      C.cast(h_out.data_ptr(), _ffi.u64p), FIELD))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    same = bool(np.array_equal(h_out.numpy()[: 1 << 16], d_out[: 1 << 16].cpu().numpy()))
+    e2e = {"value": world * n * L / (e2e_ms * 1e-3), "unit": "field-elems/s", "h2d_bytes_per_step": 32 * n,
+           "d2h_bytes_per_step": 32 * n * L, "ms_per_step": e2e_ms, "api": "hodor_cuda_lde (host pointers, pinned)",
+           "timer": "host perf_counter around the synchronous C-ABI call, max over ranks",
+           "matches_device_result": same}
+    del h_in, h_out
+
+    # ---- the sharded four-step NTT (only path with a collective), N > 1
+    sharded = None
+    if world > 1:
+        from hodor_b200.sharded import ntt_sharded
+        from hodor_b200 import field as fld
+        sharded = []
+        for ln in ([24, 26, 28] if not args.sweep else list(range(18, 29, 2))):
+            m = (1 << ln) // world
+            local = dev.to_device(synthetic_elements(m, seed=3000 + rank))
+            omega = H.Domain.new_for_size(FIELD, 1 << ln).generator
+            ms = timed(lambda: ntt_sharded(local, ln, omega, FIELD), max(2, args.steps // 2), 2) / max(2, args.steps // 2)
+            sharded.append({"log_n": ln, "ms": ms, "value": (1 << ln) / (ms * 1e-3), "unit": "field-elems/s",
+                            "hbm_frac_aggregate": 64 * (1 << ln) / (ms * 1e-3) / 1e9 / (peak_gbs * world)})
+            del local
+
+    sweep = None
+    if args.sweep and world == 1:
+        sweep = []
+        for ln in range(18, 29, 2):
+            a = dev.to_device(synthetic_elements(1 << ln, seed=ln))
+            b = dev.empty_elems(1 << ln)
+            ms = timed(lambda: dev.fft(a, b, ln, False, FIELD), 5, 3) / 5
+            sweep.append({"log_n": ln, "ms": ms, "value": (1 << ln) / (ms * 1e-3),
+                          "hbm_frac": 64 * (1 << ln) / (ms * 1e-3) / 1e9 / peak_gbs})
+            del a, b
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, dt = cpu_lde_sample(20, 2)
+        fv, _, fdt = cpu_fri_sample(20)
+        cpu_baseline = {"value": v, "unit": "field-elems/s", "cores": cores, "kind": "port",
+                        "sample": f"coset LDE 2^20 x{L} (1/16 of the workload), best of 2, {dt:.2f} s; C restatement of the "
+                                  "reference's multi-coset crossbeam path (Rust toolchain unavailable)",
+                        "fri_leaves_per_sec": fv, "fri_sample": f"FRI chain on 2^20 values, {fdt:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "ntt_field_elems_per_sec", "value": value, "unit": "field-elems/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8 x u32 Montgomery limbs, INT32 pipe)",
+            "data": "synthetic",
+            "config": {"workload": f"coset LDE 2^{LOG_N} -> 2^{LOG_N + LOG_L} (blowup {L}: {L} coset NTTs of 2^{LOG_N}) over "
+                                   "bn256.rs Fr (= BLS12-381 Fr), natural order in/out; per GPU",
+                       "field": "bls12_381_fr", "log_n": LOG_N, "lde_factor": L, "passes": 3,
+                       "l2_policy": "inputs (512 MiB) and outputs (4 GiB) exceed the 126 MB L2; no flush between steps",
+                       "parallelism": f"{world} independent polynomials, one per GPU" if world > 1 else "single GPU"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "ntt": ntt, "fri": fri,
+        }
+        if sharded is not None:
+            line["sharded_ntt"] = {"collective": "NCCL all_to_all_single (one transpose)", "scaling": "strong", "sizes": sharded}
+        if sweep is not None:
+            line["ntt_sweep"] = sweep
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--sweep", action="store_true", help="add the 2^18..2^28 NTT size sweep (configs[4])")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

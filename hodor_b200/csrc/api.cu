@@ -1,0 +1,765 @@
+// extern "C" surface of libhodor_b200.so (include/hodor_b200.h).  No torch, no CPU compute path:
+// every transform / hash entry point needs an initialised CUDA context and fails without one.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "context.h"
+
+namespace hodor {
+
+static thread_local std::string g_last_error;
+static thread_local int g_last_code = 0;
+static Ctx* g_ctx = nullptr;
+static std::mutex g_ctx_mu;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    set_error(msg);
+    g_last_code = code;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cudaGetLastError();  // clear the sticky non-fatal error state
+    g_last_code = e == cudaErrorMemoryAllocation ? HODOR_ERR_OOM : HODOR_ERR_CUDA;
+    return g_last_code;
+}
+
+Ctx* ctx() {
+    if (g_ctx == nullptr) fail(HODOR_ERR_CUDA, "hodor_cuda_init() has not been called (or failed): no GPU context, and there is no CPU path");
+    return g_ctx;
+}
+
+int Ctx::ensure_workspace(size_t bytes) {
+    if (bytes <= ws_bytes) return HODOR_OK;
+    if (ws) {
+        cudaDeviceSynchronize();
+        cudaFree(ws);
+        ws = nullptr;
+        ws_bytes = 0;
+    }
+    HODOR_CUDA_TRY(cudaMalloc(&ws, bytes));
+    ws_bytes = bytes;
+    return HODOR_OK;
+}
+
+int Ctx::ensure_io(int which, size_t bytes) {
+    if (bytes <= io_bytes[which]) return HODOR_OK;
+    if (io[which]) {
+        cudaDeviceSynchronize();
+        cudaFree(io[which]);
+        io[which] = nullptr;
+        io_bytes[which] = 0;
+    }
+    HODOR_CUDA_TRY(cudaMalloc(&io[which], bytes));
+    io_bytes[which] = bytes;
+    return HODOR_OK;
+}
+
+cudaEvent_t Ctx::take_event() {
+    if (!event_pool.empty()) {
+        cudaEvent_t e = event_pool.back();
+        event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+const FieldOps* field_ops(int field_id) {
+    switch (field_id) {
+        case HODOR_FIELD_BLS12_381_FR: return &kOpsBlsFr;
+        case HODOR_FIELD_BN254_FR: return &kOpsBn254Fr;
+        case HODOR_FIELD_STARK252: return &kOpsStark252;
+    }
+    set_error("unknown field_id");
+    return nullptr;
+}
+
+static inline Fe fe_from_u64(const uint64_t* x) {
+    Fe r;
+    memcpy(r.v, x, 32);
+    return r;
+}
+static inline void fe_to_u64(const Fe& a, uint64_t* out) { memcpy(out, a.v, 32); }
+
+// RAII device buffer for the host-pointer entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) { HODOR_CUDA_TRY(cudaMalloc(&p, bytes)); return HODOR_OK; }
+    uint4* u4() const { return (uint4*)p; }
+};
+
+static bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
+static uint32_t log2u(uint64_t n) {
+    uint32_t r = 0;
+    while (n >>= 1) r++;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// internal helpers shared by the host and device variants
+// ---------------------------------------------------------------------------------------------
+static int do_fft(Ctx& c, const FieldOps* ops, const uint4* in, uint4* out, uint32_t log_n, int coset, cudaStream_t st) {
+    Fe omega;
+    int rc = ops->h_domain_generator(log_n, omega);
+    if (rc) return fail(rc, "domain larger than the field's 2-adicity");
+    if (!coset) return ops->ntt(c, in, out, log_n, 0, omega, nullptr, nullptr, 0, nullptr, st);
+    Fe mod, one, gen, root;
+    uint32_t s, nb;
+    ops->h_constants(mod, one, gen, root, s, nb);
+    return ops->ntt(c, in, out, log_n, 0, omega, &gen, nullptr, 0, nullptr, st);
+}
+static int do_ifft(Ctx& c, const FieldOps* ops, const uint4* in, uint4* out, uint32_t log_n, int coset, cudaStream_t st) {
+    Fe omega, omega_inv;
+    int rc = ops->h_domain_generator(log_n, omega);
+    if (rc) return fail(rc, "domain larger than the field's 2-adicity");
+    ops->h_inverse(omega, omega_inv);
+    if (!coset) return ops->ntt(c, in, out, log_n, 0, omega_inv, nullptr, nullptr, 1, nullptr, st);
+    Fe mod, one, gen, root, ginv;
+    uint32_t s, nb;
+    ops->h_constants(mod, one, gen, root, s, nb);
+    ops->h_inverse(gen, ginv);
+    return ops->ntt(c, in, out, log_n, 0, omega_inv, nullptr, nullptr, 2, &ginv, st);
+}
+static int do_lde(Ctx& c, const FieldOps* ops, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_f, int coset,
+                  cudaStream_t st) {
+    if (log_f == 0) return do_fft(c, ops, in, out, log_n, coset, st);  // factor == 1 (src/polynomials/mod.rs:419,545)
+    Fe omega, coset_omega;
+    int rc = ops->h_domain_generator(log_n + log_f, coset_omega);
+    if (rc) return fail(rc, "LDE domain larger than the field's 2-adicity");
+    ops->h_domain_generator(log_n, omega);
+    Fe mod, one, gen, root;
+    uint32_t s, nb;
+    ops->h_constants(mod, one, gen, root, s, nb);
+    const Fe shift0 = coset ? gen : one;
+    return ops->ntt(c, in, out, log_n, log_f, omega, &shift0, &coset_omega, 0, nullptr, st);
+}
+static int do_merkle(Ctx& c, const FieldOps* ops, const uint4* leaves, size_t n, uint4* nodes, uint4* root, uint4* chal,
+                     cudaStream_t st) {
+    if (!is_pow2(n) || n < 2) return fail(HODOR_ERR_INVALID_ARG, "merkle: leaf count must be a power of two >= 2");
+    size_t w = 0;
+    int rc = merkle_levels(c, leaves, n, nodes, &w, st);
+    if (rc) return rc;
+    if (w == 0) return ops->merkle_tail(c, leaves, nodes, (uint32_t)n, true, root, chal, st);
+    return ops->merkle_tail(c, nodes, nodes, (uint32_t)w, false, root, chal, st);
+}
+
+}  // namespace hodor
+
+using namespace hodor;
+
+#define LOCKED_CTX()                          \
+    Ctx* c = ctx();                           \
+    if (!c) return HODOR_ERR_CUDA;            \
+    std::lock_guard<std::mutex> _lk(c->mu)
+#define GET_OPS(field_id)                         \
+    const FieldOps* ops = field_ops(field_id);    \
+    if (!ops) return HODOR_ERR_INVALID_ARG
+
+extern "C" {
+
+// ---- context -----------------------------------------------------------------------------------
+int hodor_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hodor_cuda_init(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx) {
+        if (g_ctx->device == device) return HODOR_OK;
+        return fail(HODOR_ERR_INVALID_ARG, "already initialised on another device (one process drives one GPU)");
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(HODOR_ERR_CUDA, "no CUDA device available; hodor_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(HODOR_ERR_INVALID_ARG, "device index out of range");
+    HODOR_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HODOR_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return fail(HODOR_ERR_CUDA, buf);
+    }
+    std::unique_ptr<Ctx> c(new Ctx());
+    c->device = device;
+    HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    HODOR_CUDA_TRY(cudaMalloc((void**)&c->small, 4096));
+    c->key = b2s_keyed_state();
+    g_ctx = c.release();
+    return HODOR_OK;
+}
+
+void hodor_cuda_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!g_ctx) return;
+    cudaSetDevice(g_ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : g_ctx->pow_tables) cudaFree(kv.second.block);
+    for (auto& kv : g_ctx->ntt_tables) {
+        cudaFree(kv.second.pw.block);
+        cudaFree(kv.second.tw_b_block);
+    }
+    if (g_ctx->ws) cudaFree(g_ctx->ws);
+    for (int i = 0; i < 2; i++)
+        if (g_ctx->io[i]) cudaFree(g_ctx->io[i]);
+    for (auto& r : g_ctx->prof) {
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    for (auto e : g_ctx->event_pool) cudaEventDestroy(e);
+    cudaFree(g_ctx->small);
+    cudaStreamDestroy(g_ctx->stream);
+    delete g_ctx;
+    g_ctx = nullptr;
+}
+
+const char* hodor_cuda_last_error(void) { return g_last_error.c_str(); }
+
+size_t hodor_cuda_workspace_bytes(void) {
+    Ctx* c = g_ctx;
+    return c ? c->ws_bytes + c->table_bytes + c->io_bytes[0] + c->io_bytes[1] : 0;
+}
+
+uint64_t hodor_cuda_launch_count(void) {
+    Ctx* c = g_ctx;
+    return c ? c->launches.load() : 0;
+}
+
+// ---- host scalars --------------------------------------------------------------------------------
+int hodor_field_constants(int field_id, uint64_t modulus[4], uint64_t one[4], uint64_t generator[4],
+                          uint64_t root_of_unity[4], uint32_t* s, uint32_t* num_bits, uint32_t* capacity) {
+    GET_OPS(field_id);
+    Fe m, o, g, r;
+    uint32_t ss, nb;
+    ops->h_constants(m, o, g, r, ss, nb);
+    if (modulus) fe_to_u64(m, modulus);
+    if (one) fe_to_u64(o, one);
+    if (generator) fe_to_u64(g, generator);
+    if (root_of_unity) fe_to_u64(r, root_of_unity);
+    if (s) *s = ss;
+    if (num_bits) *num_bits = nb;
+    if (capacity) *capacity = nb - 1;
+    return HODOR_OK;
+}
+int hodor_domain_generator(int field_id, uint32_t log_n, uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe g;
+    int rc = ops->h_domain_generator(log_n, g);
+    if (rc) return fail(rc, "domain larger than the field's 2-adicity");
+    fe_to_u64(g, out);
+    return HODOR_OK;
+}
+int hodor_field_mul(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    ops->h_mul(fe_from_u64(a), fe_from_u64(b), r);
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_field_add(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    ops->h_add(fe_from_u64(a), fe_from_u64(b), r);
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_field_sub(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    ops->h_sub(fe_from_u64(a), fe_from_u64(b), r);
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_field_pow(int field_id, const uint64_t a[4], uint64_t e, uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    ops->h_pow(fe_from_u64(a), e, r);
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_field_inverse(int field_id, const uint64_t a[4], uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    int rc = ops->h_inverse(fe_from_u64(a), r);
+    if (rc) return fail(rc, "inverse of zero");
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_field_from_repr(int field_id, const uint64_t plain[4], uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    ops->h_from_repr(fe_from_u64(plain), r);
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_field_into_repr(int field_id, const uint64_t mont[4], uint64_t out[4]) {
+    GET_OPS(field_id);
+    Fe r;
+    ops->h_into_repr(fe_from_u64(mont), r);
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+int hodor_root_to_challenge(const uint8_t root[32], uint64_t out[4], int field_id) {
+    GET_OPS(field_id);
+    Fe r;
+    int rc = ops->h_root_to_challenge(root, r);
+    if (rc) return fail(rc, "digest does not reduce into the field");
+    fe_to_u64(r, out);
+    return HODOR_OK;
+}
+
+// ---- memory --------------------------------------------------------------------------------------
+void* hodor_cuda_malloc(size_t bytes) {
+    if (!ctx()) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMalloc");
+        return nullptr;
+    }
+    return p;
+}
+void hodor_cuda_free(void* dptr) {
+    if (dptr) cudaFree(dptr);
+}
+void* hodor_cuda_host_alloc(size_t bytes) {
+    if (!ctx()) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaHostAlloc");
+        return nullptr;
+    }
+    return p;
+}
+void hodor_cuda_host_free(void* hptr) {
+    if (hptr) cudaFreeHost(hptr);
+}
+static cudaStream_t pick_stream(Ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
+int hodor_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream) {
+    Ctx* c = ctx();
+    if (!c) return HODOR_ERR_CUDA;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, pick_stream(c, stream)));
+    return HODOR_OK;
+}
+int hodor_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream) {
+    Ctx* c = ctx();
+    if (!c) return HODOR_ERR_CUDA;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, pick_stream(c, stream)));
+    return HODOR_OK;
+}
+int hodor_cuda_stream_synchronize(void* stream) {
+    Ctx* c = ctx();
+    if (!c) return HODOR_ERR_CUDA;
+    HODOR_CUDA_TRY(cudaStreamSynchronize(pick_stream(c, stream)));
+    return HODOR_OK;
+}
+
+// ---- device variants -------------------------------------------------------------------------------
+int hodor_cuda_ntt_dev(const void* d_in, void* d_out, uint32_t log_n, const uint64_t omega[4], int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return ops->ntt(*c, (const uint4*)d_in, (uint4*)d_out, log_n, 0, fe_from_u64(omega), nullptr, nullptr, 0, nullptr,
+                    pick_stream(c, stream));
+}
+int hodor_cuda_fft_dev(const void* d_in, void* d_out, uint32_t log_n, int coset, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return do_fft(*c, ops, (const uint4*)d_in, (uint4*)d_out, log_n, coset, pick_stream(c, stream));
+}
+int hodor_cuda_ifft_dev(const void* d_in, void* d_out, uint32_t log_n, int coset, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return do_ifft(*c, ops, (const uint4*)d_in, (uint4*)d_out, log_n, coset, pick_stream(c, stream));
+}
+int hodor_cuda_lde_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, void* d_out, int field_id,
+                       void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (d_coeffs == d_out && log_factor) return fail(HODOR_ERR_INVALID_ARG, "lde: input and output must not alias");
+    return do_lde(*c, ops, (const uint4*)d_coeffs, (uint4*)d_out, log_n, log_factor, coset, pick_stream(c, stream));
+}
+int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes, void* d_root, void* d_challenge,
+                                int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return do_merkle(*c, ops, (const uint4*)d_leaves, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,
+                     pick_stream(c, stream));
+}
+int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
+                            const void* d_challenge, void* d_out, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (!is_pow2(n) || n < 2 || !is_pow2(initial_domain_size) || (initial_domain_size >> layer) != n)
+        return fail(HODOR_ERR_INVALID_ARG, "fri_fold: n must equal initial_domain_size >> layer, both powers of two");
+    return ops->fri_fold(*c, (const uint4*)d_in, n, log2u(initial_domain_size), layer, (const uint4*)d_challenge,
+                         (uint4*)d_out, pick_stream(c, stream));
+}
+int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
+                               void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, pick_stream(c, stream));
+}
+int hodor_cuda_ntt_shard_cols_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
+                                  const uint64_t omega[4], int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_g > 4 || log_n < 2 * log_g || rank >= (1u << log_g)) return fail(HODOR_ERR_INVALID_ARG, "shard_cols: bad geometry");
+    // local transform of length m = n/G with root omega^G, then B_g[k] *= (omega^g)^k
+    Fe w = fe_from_u64(omega), wm, wg;
+    ops->h_pow(w, (uint64_t)1 << log_g, wm);
+    ops->h_pow(w, rank, wg);
+    return ops->ntt(*c, (const uint4*)d_in, (uint4*)d_out, log_n - log_g, 0, wm, nullptr, nullptr, log_g ? 3 : 0, &wg,
+                    pick_stream(c, stream));
+}
+int hodor_cuda_ntt_shard_rows_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
+                                  const uint64_t omega[4], int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return ops->shard_rows(*c, (const uint4*)d_in, (uint4*)d_out, log_n, log_g, rank, fe_from_u64(omega),
+                           pick_stream(c, stream));
+}
+
+// ---- host variants: H2D, the device variant, D2H ---------------------------------------------------
+// Staging goes through the context's grow-only device buffers (io[0] input, io[1] output), so a
+// caller looping over same-sized vectors pays cudaMalloc once.
+static int host_inplace(Ctx* c, uint64_t* a, size_t n, int (*body)(Ctx&, uint4*, void*), void* arg) {
+    int rc = c->ensure_io(0, n * 32);
+    if (rc) return rc;
+    uint4* d = (uint4*)c->io[0];
+    HODOR_CUDA_TRY(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = body(*c, d, arg);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(a, d, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+
+int hodor_cuda_ntt(uint64_t* a, uint32_t log_n, const uint64_t omega[4], int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 32) return fail(HODOR_ERR_INVALID_ARG, "log_n > 32");
+    struct A { const FieldOps* ops; uint32_t log_n; Fe omega; } arg{ops, log_n, fe_from_u64(omega)};
+    return host_inplace(c, a, (size_t)1 << log_n, [](Ctx& cc, uint4* d, void* p) {
+        A* a = (A*)p;
+        return a->ops->ntt(cc, d, d, a->log_n, 0, a->omega, nullptr, nullptr, 0, nullptr, cc.stream);
+    }, &arg);
+}
+int hodor_cuda_fft(uint64_t* a, uint32_t log_n, int coset, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 32) return fail(HODOR_ERR_INVALID_ARG, "log_n > 32");
+    struct A { const FieldOps* ops; uint32_t log_n; int coset; } arg{ops, log_n, coset};
+    return host_inplace(c, a, (size_t)1 << log_n, [](Ctx& cc, uint4* d, void* p) {
+        A* a = (A*)p;
+        return do_fft(cc, a->ops, d, d, a->log_n, a->coset, cc.stream);
+    }, &arg);
+}
+int hodor_cuda_ifft(uint64_t* a, uint32_t log_n, int coset, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 32) return fail(HODOR_ERR_INVALID_ARG, "log_n > 32");
+    struct A { const FieldOps* ops; uint32_t log_n; int coset; } arg{ops, log_n, coset};
+    return host_inplace(c, a, (size_t)1 << log_n, [](Ctx& cc, uint4* d, void* p) {
+        A* a = (A*)p;
+        return do_ifft(cc, a->ops, d, d, a->log_n, a->coset, cc.stream);
+    }, &arg);
+}
+int hodor_cuda_distribute_powers(uint64_t* a, uint64_t n, const uint64_t g[4], int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (n == 0) return HODOR_OK;
+    struct A { const FieldOps* ops; size_t n; Fe g; } arg{ops, (size_t)n, fe_from_u64(g)};
+    return host_inplace(c, a, (size_t)n, [](Ctx& cc, uint4* d, void* p) {
+        A* a = (A*)p;
+        return a->ops->scale_pow(cc, d, a->n, a->g, cc.stream);
+    }, &arg);
+}
+int hodor_cuda_lde(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint64_t* out, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 32 || log_n + log_factor > 34) return fail(HODOR_ERR_INVALID_ARG, "lde too large");
+    const size_t n = (size_t)1 << log_n, total = n << log_factor;
+    int rc = c->ensure_io(0, n * 32);
+    if (rc) return rc;
+    rc = c->ensure_io(1, total * 32);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], coeffs, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = do_lde(*c, ops, (const uint4*)c->io[0], (uint4*)c->io[1], log_n, log_factor, coset, c->stream);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[1], total * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (n == 0) return HODOR_OK;
+    const size_t nb = op == 3 ? 1 : (size_t)n;
+    int rc = c->ensure_io(0, n * 32);
+    if (rc) return rc;
+    rc = c->ensure_io(1, nb * 32);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[1], b, nb * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = ops->elementwise(*c, op, (const uint4*)c->io[0], (const uint4*)c->io[1], (uint4*)c->io[0], n, c->stream);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[0], n * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+int hodor_cuda_merkle_build(const uint64_t* leaves, uint64_t n, uint8_t* nodes, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (!is_pow2(n) || n < 2) return fail(HODOR_ERR_INVALID_ARG, "merkle: leaf count must be a power of two >= 2");
+    int rc = c->ensure_io(0, n * 32);
+    if (rc) return rc;
+    rc = c->ensure_io(1, n * 32);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], leaves, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = do_merkle(*c, ops, (const uint4*)c->io[0], n, (uint4*)c->io[1], nullptr, nullptr, c->stream);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(nodes, c->io[1], n * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+
+// ---- per-kernel timing (bench.py's live roofline) ------------------------------------------------------
+int hodor_cuda_profile_begin(void) {
+    LOCKED_CTX();
+    for (auto& r : c->prof) {
+        c->event_pool.push_back(r.start);
+        c->event_pool.push_back(r.stop);
+    }
+    c->prof.clear();
+    c->profiling = true;
+    return HODOR_OK;
+}
+int hodor_cuda_profile_end(char* json_out, size_t cap) {
+    LOCKED_CTX();
+    c->profiling = false;
+    HODOR_CUDA_TRY(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<uint64_t, double>> agg;  // name -> (count, total ms)
+    for (auto& r : c->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        auto& a = agg[r.name];
+        a.first += 1;
+        a.second += ms;
+    }
+    std::string js = "[";
+    bool first = true;
+    for (auto& kv : agg) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s{\"name\": \"%s\", \"count\": %llu, \"total_ms\": %.6f}", first ? "" : ", ",
+                 kv.first.c_str(), (unsigned long long)kv.second.first, kv.second.second);
+        js += buf;
+        first = false;
+    }
+    js += "]";
+    for (auto& r : c->prof) {
+        c->event_pool.push_back(r.start);
+        c->event_pool.push_back(r.stop);
+    }
+    c->prof.clear();
+    if (json_out && cap) {
+        if (js.size() + 1 > cap) return fail(HODOR_ERR_INVALID_ARG, "profile buffer too small");
+        memcpy(json_out, js.c_str(), js.size() + 1);
+    }
+    return (int)agg.size();
+}
+
+// ---- FRI commit chain --------------------------------------------------------------------------------
+struct hodor_fri_proto {
+    int field_id = 0;
+    uint64_t n = 0;
+    uint32_t lde_factor = 0, out_coeffs = 0;
+    int steps = 0;
+    uint4* block = nullptr;      // one allocation for everything below
+    const uint4* lde = nullptr;  // layer-0 values (borrowed device pointer, or inside `owned_lde`)
+    uint4* owned_lde = nullptr;
+    std::vector<uint4*> nodes;   // nodes[0] = l0, nodes[i] = intermediate i-1
+    std::vector<uint4*> values;  // values[0] = lde, values[i] = intermediate i-1
+    uint4* roots = nullptr;      // steps + 1 digests
+    uint4* chal = nullptr;       // steps + 1 elements (the last one is never used by a fold)
+    uint4* final_coeffs = nullptr;  // ifft of the last layer (n >> steps elements)
+    uint4* path = nullptr;       // scratch for queries: 64 digests + 1 element
+};
+
+static void fri_destroy(hodor_fri_proto* p) {
+    if (!p) return;
+    if (p->block) cudaFree(p->block);
+    if (p->owned_lde) cudaFree(p->owned_lde);
+    delete p;
+}
+
+hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
+                                       int lde_on_device, int field_id) {
+    Ctx* c = ctx();
+    if (!c) return nullptr;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const FieldOps* ops = field_ops(field_id);
+    if (!ops) return nullptr;
+    // the reference's asserts (src/fri/fri_on_values.rs:42-46) and its roots.pop() on an empty vec
+    if (!is_pow2(n) || n < 2 || !is_pow2(lde_factor) || !is_pow2(out_coeffs) || lde_factor > n ||
+        (n / lde_factor) / out_coeffs == 0) {
+        fail(HODOR_ERR_INVALID_ARG, "fri_commit: n, lde_factor, out_coeffs must be powers of two with n/lde_factor >= out_coeffs");
+        return nullptr;
+    }
+    const int steps = (int)log2u((n / lde_factor) / out_coeffs);
+    if (steps < 1) {
+        fail(HODOR_ERR_INVALID_ARG, "fri_commit: zero folding steps (the reference panics here: roots.pop() on empty)");
+        return nullptr;
+    }
+    Fe probe;
+    if (ops->h_domain_generator(log2u(n), probe)) {
+        fail(HODOR_ERR_DOMAIN, "fri_commit: domain larger than the field's 2-adicity");
+        return nullptr;
+    }
+    std::unique_ptr<hodor_fri_proto, void (*)(hodor_fri_proto*)> p(new hodor_fri_proto(), fri_destroy);
+    p->field_id = field_id;
+    p->n = n;
+    p->lde_factor = lde_factor;
+    p->out_coeffs = out_coeffs;
+    p->steps = steps;
+    cudaStream_t st = c->stream;
+    if (lde_on_device) {
+        p->lde = (const uint4*)lde;
+    } else {
+        if (cudaMalloc((void**)&p->owned_lde, n * 32) != cudaSuccess) {
+            cuda_fail(cudaGetLastError(), "cudaMalloc(lde)");
+            return nullptr;
+        }
+        if (cudaMemcpyAsync(p->owned_lde, lde, n * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(lde)");
+            return nullptr;
+        }
+        p->lde = p->owned_lde;
+    }
+    // layout (in 32-byte slots): l0 nodes n | per layer: nodes + values | roots | challenges | final | path scratch
+    size_t slots = n;
+    for (int i = 0; i < steps; i++) slots += 2 * (n >> (i + 1));
+    const size_t last = n >> steps;
+    slots += 2 * (size_t)(steps + 1) + last + 80;
+    if (cudaMalloc((void**)&p->block, slots * 32) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaMalloc(fri)");
+        return nullptr;
+    }
+    uint4* cur = p->block;
+    auto take = [&](size_t count) {
+        uint4* r = cur;
+        cur += 2 * count;
+        return r;
+    };
+    p->nodes.push_back(take(n));
+    p->values.push_back(const_cast<uint4*>(p->lde));
+    for (int i = 0; i < steps; i++) {
+        p->nodes.push_back(take(n >> (i + 1)));
+        p->values.push_back(take(n >> (i + 1)));
+    }
+    p->roots = take(steps + 1);
+    p->chal = take(steps + 1);
+    p->final_coeffs = take(last);
+    p->path = take(80);
+
+    int rc = do_merkle(*c, ops, p->lde, n, p->nodes[0], p->roots, p->chal, st);
+    const uint32_t log_n0 = log2u(n);
+    for (int i = 0; i < steps && !rc; i++) {
+        const size_t m = n >> i;
+        rc = ops->fri_fold(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], st);
+        if (rc) break;
+        rc = do_merkle(*c, ops, p->values[i + 1], m / 2, p->nodes[i + 1], p->roots + 2 * (i + 1), p->chal + 2 * (i + 1), st);
+    }
+    if (!rc) rc = do_ifft(*c, ops, p->values[steps], p->final_coeffs, log2u(last), 0, st);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "fri_commit sync");
+    if (rc) return nullptr;
+    return p.release();
+}
+
+void hodor_cuda_fri_free(hodor_fri_proto* p) {
+    Ctx* c = g_ctx;
+    if (c) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        cudaStreamSynchronize(c->stream);
+        fri_destroy(p);
+    } else {
+        fri_destroy(p);
+    }
+}
+int hodor_cuda_fri_num_steps(const hodor_fri_proto* p) { return p ? p->steps : HODOR_ERR_INVALID_ARG; }
+uint64_t hodor_cuda_fri_layer_size(const hodor_fri_proto* p, uint32_t layer) {
+    if (!p || layer > (uint32_t)p->steps) return 0;
+    return p->n >> layer;
+}
+int hodor_cuda_fri_summary(const hodor_fri_proto* p, uint8_t* roots, uint64_t* challenges, uint64_t* final_coeffs) {
+    LOCKED_CTX();
+    if (!p) return fail(HODOR_ERR_INVALID_ARG, "null handle");
+    cudaStream_t st = c->stream;
+    if (roots) HODOR_CUDA_TRY(cudaMemcpyAsync(roots, p->roots, (size_t)(p->steps + 1) * 32, cudaMemcpyDeviceToHost, st));
+    if (challenges) HODOR_CUDA_TRY(cudaMemcpyAsync(challenges, p->chal, (size_t)p->steps * 32, cudaMemcpyDeviceToHost, st));
+    if (final_coeffs)
+        HODOR_CUDA_TRY(cudaMemcpyAsync(final_coeffs, p->final_coeffs, (size_t)p->out_coeffs * 32, cudaMemcpyDeviceToHost, st));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+    return HODOR_OK;
+}
+int hodor_cuda_fri_layer(const hodor_fri_proto* p, uint32_t layer, uint8_t* nodes, uint64_t* values) {
+    LOCKED_CTX();
+    if (!p || layer > (uint32_t)p->steps) return fail(HODOR_ERR_INVALID_ARG, "bad handle or layer");
+    const size_t m = p->n >> layer;
+    cudaStream_t st = c->stream;
+    if (nodes) HODOR_CUDA_TRY(cudaMemcpyAsync(nodes, p->nodes[layer], m * 32, cudaMemcpyDeviceToHost, st));
+    if (values) HODOR_CUDA_TRY(cudaMemcpyAsync(values, p->values[layer], m * 32, cudaMemcpyDeviceToHost, st));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+    return HODOR_OK;
+}
+int hodor_cuda_fri_query(const hodor_fri_proto* p, uint32_t layer, uint64_t natural_index, uint64_t value[4], uint8_t* path) {
+    LOCKED_CTX();
+    if (!p || layer > (uint32_t)p->steps) return fail(HODOR_ERR_INVALID_ARG, "bad handle or layer");
+    const size_t m = p->n >> layer;
+    if (natural_index >= m) return fail(HODOR_ERR_INVALID_ARG, "query index out of range");  // reference: assert!
+    cudaStream_t st = c->stream;
+    int rc = merkle_path_gather(*c, p->nodes[layer], p->values[layer], m, natural_index, p->path, st);
+    if (rc) return rc;
+    const int len = (int)log2u(m);
+    if (path) HODOR_CUDA_TRY(cudaMemcpyAsync(path, p->path, (size_t)len * 32, cudaMemcpyDeviceToHost, st));
+    if (value) HODOR_CUDA_TRY(cudaMemcpyAsync(value, p->values[layer] + 2 * natural_index, 32, cudaMemcpyDeviceToHost, st));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+    return len;
+}
+int hodor_cuda_fri_commit_host(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs, uint8_t* l0_nodes,
+                               uint8_t** layer_nodes, uint64_t** layer_values, uint64_t* challenges, uint8_t* final_root,
+                               uint64_t* final_coeffs, int field_id) {
+    hodor_fri_proto* p = hodor_cuda_fri_commit(lde, n, lde_factor, out_coeffs, 0, field_id);
+    if (!p) return g_last_code ? g_last_code : HODOR_ERR_CUDA;
+    int rc = HODOR_OK;
+    std::vector<uint8_t> roots((size_t)(p->steps + 1) * 32);
+    rc = hodor_cuda_fri_summary(p, roots.data(), challenges, final_coeffs);
+    if (!rc && final_root) memcpy(final_root, roots.data() + (size_t)p->steps * 32, 32);
+    if (!rc && l0_nodes) rc = hodor_cuda_fri_layer(p, 0, l0_nodes, nullptr);
+    for (int i = 0; i < p->steps && !rc; i++)
+        rc = hodor_cuda_fri_layer(p, (uint32_t)i + 1, layer_nodes ? layer_nodes[i] : nullptr, layer_values ? layer_values[i] : nullptr);
+    const int steps = p->steps;
+    hodor_cuda_fri_free(p);
+    return rc ? rc : steps;
+}
+
+}  // extern "C"

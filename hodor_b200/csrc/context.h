@@ -1,0 +1,150 @@
+// Process-wide context of the hodor_b200 library: one GPU, one default stream, a grow-only
+// workspace, a cache of twiddle / coset-power tables.  Host-only header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hodor_b200.h"
+#include "field.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+namespace hodor {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define HODOR_CUDA_TRY(expr)                                  \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);   \
+    } while (0)
+
+// base^e for one or several bases, e in [0, 2^bits): lo[b][e & mask] * hi[b][e >> lo_bits]
+struct PowTables {
+    uint4* block = nullptr;  // one allocation: bases | lo tables | hi tables
+    uint4* lo = nullptr;
+    uint4* hi = nullptr;
+    uint32_t lo_bits = 0, hi_bits = 0, count = 0;
+    size_t bytes = 0;
+    TwoLevel two_level() const { return TwoLevel{lo, hi, lo_bits}; }
+    uint32_t stride_lo() const { return 1u << lo_bits; }
+    uint32_t stride_hi() const { return 1u << hi_bits; }
+};
+
+struct NttTables {
+    PowTables pw;            // powers of omega, exponents [0, 2^log_n)
+    uint4* tw_b[10] = {};    // tw_b[B][x] = omega^(x << (log_n - B)), B in 6..9 (as used by the plan)
+    uint4* tw_b_block = nullptr;
+    Fe wr[7];                // omega_16^k, k = 1..7
+    size_t bytes = 0;
+};
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    uint4* small = nullptr;  // 4 KiB of device scratch for scalars
+    B2sState key;
+    std::map<std::string, NttTables> ntt_tables;
+    std::map<std::string, PowTables> pow_tables;
+    size_t table_bytes = 0;
+    std::atomic<uint64_t> launches{0};
+
+    // host-pointer entry points stage through these grow-only device buffers
+    void* io[2] = {nullptr, nullptr};
+    size_t io_bytes[2] = {0, 0};
+
+    // optional per-launch timing (bench.py's live roofline): events around every kernel
+    struct ProfRec {
+        const char* name;
+        cudaEvent_t start, stop;
+    };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+
+    int ensure_workspace(size_t bytes);
+    int ensure_io(int which, size_t bytes);
+    cudaEvent_t take_event();
+};
+
+// RAII: brackets one kernel launch with events when profiling is on
+struct ProfScope {
+    Ctx& c;
+    cudaStream_t st;
+    long idx = -1;
+    ProfScope(Ctx& ctx_, cudaStream_t st_, const char* name) : c(ctx_), st(st_) {
+        c.launches++;
+        if (!c.profiling) return;
+        Ctx::ProfRec r{name, c.take_event(), c.take_event()};
+        cudaEventRecord(r.start, st);
+        c.prof.push_back(r);
+        idx = (long)c.prof.size() - 1;
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(c.prof[idx].stop, st);
+    }
+};
+
+Ctx* ctx();  // nullptr (and error set) when not initialised
+
+struct NttPlan {
+    int passes = 0;  // 0 => single-block kernel
+    int b[4] = {0, 0, 0, 0};
+};
+inline NttPlan make_plan(uint32_t log_n) {
+    NttPlan p;
+    if (log_n <= 11) return p;
+    p.passes = (int)((log_n + 8) / 9);
+    const int base = (int)log_n / p.passes, rem = (int)log_n % p.passes;
+    for (int i = 0; i < p.passes; i++) p.b[i] = base + (i < rem ? 1 : 0);
+    return p;
+}
+
+// Per-field entry points (one translation unit per field instantiates them).
+struct FieldOps {
+    // host scalar arithmetic on 8 x u32 Montgomery elements
+    void (*h_mul)(const Fe&, const Fe&, Fe&);
+    void (*h_add)(const Fe&, const Fe&, Fe&);
+    void (*h_sub)(const Fe&, const Fe&, Fe&);
+    void (*h_pow)(const Fe&, uint64_t, Fe&);
+    int (*h_inverse)(const Fe&, Fe&);
+    void (*h_from_repr)(const Fe&, Fe&);
+    void (*h_into_repr)(const Fe&, Fe&);
+    void (*h_constants)(Fe& modulus, Fe& one, Fe& generator, Fe& root, uint32_t& s, uint32_t& num_bits);
+    int (*h_domain_generator)(uint32_t log_n, Fe& out);
+    int (*h_root_to_challenge)(const uint8_t* root, Fe& out);
+
+    // device work, enqueued on `st`
+    // general transform: `log_l` cosets; shift0/step null => no input scaling (then log_l == 0);
+    // out_mode 0 none, 1 multiply by n^-1 (ifft), 2 multiply by n^-1 * out_g^k (icoset)
+    int (*ntt)(Ctx&, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_l, const Fe& omega, const Fe* shift0,
+               const Fe* step, int out_mode, const Fe* out_g, cudaStream_t st);
+    int (*scale_pow)(Ctx&, uint4* a, size_t n, const Fe& g, cudaStream_t st);
+    int (*elementwise)(Ctx&, int op, const uint4* a, const uint4* b, uint4* out, size_t n, cudaStream_t st);
+    int (*merkle_tail)(Ctx&, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
+                       cudaStream_t st);
+    int (*fri_fold)(Ctx&, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
+                    cudaStream_t st);
+    int (*shard_rows)(Ctx&, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_g, uint32_t rank, const Fe& omega,
+                      cudaStream_t st);
+};
+extern const FieldOps kOpsBlsFr, kOpsBn254Fr, kOpsStark252;
+const FieldOps* field_ops(int field_id);
+
+// field independent Merkle levels (merkle_common.cu)
+int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st);
+int merkle_path_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
+                       cudaStream_t st);
+
+}  // namespace hodor

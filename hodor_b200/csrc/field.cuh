@@ -1,0 +1,425 @@
+// 256-bit prime-field arithmetic for sm_100a: 8 x u32 limbs, Montgomery form with R = 2^256,
+// canonical representatives -- the in-memory format of ff_ce's derive(PrimeField) for a 4 x u64
+// repr (reference: src/bn256.rs:4-7; Montgomery/R evidence src/experiments/square_root_calculator/
+// fp2.rs:10-22).  One field per template instantiation; no runtime dispatch inside kernels.
+//
+// The multiplier keeps two carry-save accumulators, one for the even-indexed and one for the
+// odd-indexed limb products, so that every 32x32->64 product lands on a 64-bit aligned register
+// pair (ptxas then fuses each mad.lo.cc/madc.hi.cc pair into one IMAD.WIDE.U32.X).  The division
+// by 2^32 after every reduction step is a role swap of the two accumulators, not a data move.
+//
+// The same algorithm body compiles for the host (carry chains emulated with 64-bit arithmetic)
+// so that it can be unit-tested without a GPU; the product never calls the host variant.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+#else
+#define HD inline
+#define DEV inline
+#endif
+
+namespace hodor {
+
+enum FieldId : int { FIELD_BLS12_381_FR = 0, FIELD_BN254_FR = 1, FIELD_STARK252 = 2, NUM_FIELDS = 3 };
+
+struct Fe {
+    uint32_t v[8];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Field parameter packs.  Limbs little-endian, 32 bit.
+// ---------------------------------------------------------------------------------------------
+struct BlsFr {  // what the reference's src/bn256.rs declares: the BLS12-381 scalar field
+    static constexpr int ID = FIELD_BLS12_381_FR;
+    static constexpr uint32_t INV = 0xffffffffu;  // -p^-1 mod 2^32
+    static constexpr int S = 32, NUM_BITS = 255, GENERATOR = 7;
+    HD static constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return t[i];
+    }
+    HD static constexpr uint32_t ONE(int i) {  // R mod p
+        constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return t[i];
+    }
+    HD static constexpr uint32_t R2(int i) {  // R^2 mod p
+        constexpr uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return t[i];
+    }
+};
+
+struct Bn254Fr {  // the field usually called "bn256 Fr" (not what src/bn256.rs holds)
+    static constexpr int ID = FIELD_BN254_FR;
+    static constexpr uint32_t INV = 0xefffffffu;
+    static constexpr int S = 28, NUM_BITS = 254, GENERATOR = 5;
+    HD static constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                   0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                   0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return t[i];
+    }
+};
+
+struct Stark252 {  // src/experiments/mod.rs:18-21
+    static constexpr int ID = FIELD_STARK252;
+    static constexpr uint32_t INV = 0xffffffffu;
+    static constexpr int S = 192, NUM_BITS = 252, GENERATOR = 3;
+    HD static constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u,
+                                   0x00000000u, 0x00000000u, 0x00000011u, 0x08000000u};
+        return t[i];
+    }
+    HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t t[8] = {0xffffffe1u, 0xffffffffu, 0xffffffffu, 0xffffffffu,
+                                   0xffffffffu, 0xffffffffu, 0xfffffdf0u, 0x07ffffffu};
+        return t[i];
+    }
+    HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0x7e000401u, 0xfffffd73u, 0x330fffffu, 0x00000001u,
+                                   0xff6f8000u, 0xffffffffu, 0x5e008810u, 0x07ffd4abu};
+        return t[i];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Carry-chain rows.  Device: one asm statement per chain.  Host: 64-bit emulation.
+// ---------------------------------------------------------------------------------------------
+
+// acc[0..7] (as four 64-bit columns) += x0*y, x2*y<<64, x4*y<<128, x6*y<<192 ; top += carry out
+HD void row_mad(uint32_t (&acc)[8], uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y, uint32_t& top) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+        "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+        "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(top)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+#else
+    const uint32_t x[4] = {x0, x2, x4, x6};
+    uint64_t c = 0;
+    for (int k = 0; k < 4; k++) {
+        uint64_t prod = (uint64_t)x[k] * y;
+        uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)prod + c;
+        acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * k + 1] + (prod >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    top += (uint32_t)c;
+#endif
+}
+
+// Same, but the carry out is provably zero (see mont_mul) and dropped.
+HD void row_mad_nocarry(uint32_t (&acc)[8], uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %8,  %12, %0;\n\t"
+        "madc.hi.cc.u32  %1, %8,  %12, %1;\n\t"
+        "madc.lo.cc.u32  %2, %9,  %12, %2;\n\t"
+        "madc.hi.cc.u32  %3, %9,  %12, %3;\n\t"
+        "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32  %6, %11, %12, %6;\n\t"
+        "madc.hi.u32     %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7])
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+#else
+    uint32_t dummy = 0;
+    row_mad(acc, x0, x2, x4, x6, y, dummy);
+#endif
+}
+
+// acc[0..7] = x0*y, x2*y<<64, ... (no accumulate, no carries)
+HD void row_mul(uint32_t (&acc)[8], uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
+#ifdef __CUDA_ARCH__
+    asm("mul.lo.u32 %0, %8,  %12;\n\t"
+        "mul.hi.u32 %1, %8,  %12;\n\t"
+        "mul.lo.u32 %2, %9,  %12;\n\t"
+        "mul.hi.u32 %3, %9,  %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+          "=r"(acc[7])
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+#else
+    const uint32_t x[4] = {x0, x2, x4, x6};
+    for (int k = 0; k < 4; k++) {
+        uint64_t prod = (uint64_t)x[k] * y;
+        acc[2 * k] = (uint32_t)prod;
+        acc[2 * k + 1] = (uint32_t)(prod >> 32);
+    }
+#endif
+}
+
+// The role swap: `lo` is the accumulator that becomes the new low-aligned one, `sh` the one whose
+// word 0 is known to be zero and which is being divided by 2^32 twice (once by dropping word 0,
+// once by the accumulator offset).  Computes
+//     lo[0] += sh[1]                          (carry c)
+//     sh'   = (sh >> 64) + c + (x1*y, x3*y<<64, x5*y<<128, x7*y<<192)
+HD void row_shift_mad(uint32_t (&lo)[8], uint32_t (&sh)[8], uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7,
+                      uint32_t y) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32      %0, %0, %2;\n\t"
+        "madc.lo.cc.u32  %1, %9,  %13, %3;\n\t"
+        "madc.hi.cc.u32  %2, %9,  %13, %4;\n\t"
+        "madc.lo.cc.u32  %3, %10, %13, %5;\n\t"
+        "madc.hi.cc.u32  %4, %10, %13, %6;\n\t"
+        "madc.lo.cc.u32  %5, %11, %13, %7;\n\t"
+        "madc.hi.cc.u32  %6, %11, %13, %8;\n\t"
+        "madc.lo.cc.u32  %7, %12, %13, 0;\n\t"
+        "madc.hi.u32     %8, %12, %13, 0;"
+        : "+r"(lo[0]), "+r"(sh[0]), "+r"(sh[1]), "+r"(sh[2]), "+r"(sh[3]), "+r"(sh[4]), "+r"(sh[5]), "+r"(sh[6]),
+          "+r"(sh[7])
+        : "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+#else
+    uint64_t t = (uint64_t)lo[0] + sh[1];
+    lo[0] = (uint32_t)t;
+    uint64_t c = t >> 32;
+    const uint32_t x[4] = {x1, x3, x5, x7};
+    uint32_t in[8] = {sh[2], sh[3], sh[4], sh[5], sh[6], sh[7], 0, 0};
+    for (int k = 0; k < 4; k++) {
+        uint64_t prod = (uint64_t)x[k] * y;
+        uint64_t l = (uint64_t)in[2 * k] + (uint32_t)prod + c;
+        sh[2 * k] = (uint32_t)l;
+        uint64_t h = (uint64_t)in[2 * k + 1] + (prod >> 32) + (l >> 32);
+        sh[2 * k + 1] = (uint32_t)h;
+        c = h >> 32;
+    }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// r = a + b (no reduction), returns carry;   r = a - b, returns borrow (1 if a < b)
+// ---------------------------------------------------------------------------------------------
+HD uint32_t add256(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t carry;
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(carry)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    carry = (uint32_t)c;
+#endif
+    return carry;
+}
+
+HD uint32_t sub256(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t borrow;
+#ifdef __CUDA_ARCH__
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(borrow)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    borrow &= 1u;  // subc of 0-0-borrow gives 0xffffffff
+#else
+    uint64_t bw = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] - b[i] - bw;
+        r[i] = (uint32_t)d;
+        bw = (d >> 32) & 1;
+    }
+    borrow = (uint32_t)bw;
+#endif
+    return borrow;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Field<F>: canonical Montgomery arithmetic
+// ---------------------------------------------------------------------------------------------
+template <class F>
+struct Field {
+    // The modulus lives in vector registers: ptxas only fuses mad.lo.cc/madc.hi.cc pairs into
+    // IMAD.WIDE.U32.X when both factors are registers.  `opaque_zero` must be 0 at run time but
+    // unknown (and per-thread) at compile time, e.g. threadIdx.x & kernel_param_zero; with the
+    // default 0 the limbs constant-fold into immediates.
+    uint32_t p[8];
+    HD explicit Field(uint32_t opaque_zero = 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = F::P(i) | opaque_zero;
+    }
+
+    HD static Fe one() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = F::ONE(i);
+        return r;
+    }
+    HD static Fe r2() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = F::R2(i);
+        return r;
+    }
+    HD static Fe zero() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r;
+    }
+
+    // t in [0, 2p) -> [0, p)
+    HD void reduce_once(uint32_t (&t)[8]) const {
+        uint32_t u[8];
+        uint32_t borrow = sub256(u, t, p);
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = borrow ? t[i] : u[i];
+    }
+
+    HD Fe add(const Fe& a, const Fe& b) const {
+        Fe r;
+        add256(r.v, a.v, b.v);  // p < 2^255: a + b < 2^256, no carry
+        reduce_once(r.v);
+        return r;
+    }
+    HD Fe sub(const Fe& a, const Fe& b) const {
+        Fe r;
+        uint32_t borrow = sub256(r.v, a.v, b.v);
+        uint32_t u[8];
+        add256(u, r.v, p);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = borrow ? u[i] : r.v[i];
+        return r;
+    }
+    HD Fe neg(const Fe& a) const { return sub(zero(), a); }
+
+    // x / 2 in the field.  Linear, so it is the same operation on Montgomery representations.
+    HD Fe halve(const Fe& a) const {
+        uint32_t q[8], t[8];
+        const uint32_t odd = a.v[0] & 1u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = odd ? p[i] : 0u;
+        add256(t, a.v, q);  // a + p < 2p < 2^256
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 7; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+        r.v[7] = t[7] >> 1;
+        return r;
+    }
+
+    // Montgomery product a*b*R^-1 mod p, canonical.  Inputs must be < p.
+    //
+    // Invariant kept across the 8 reduction steps: running total T = E + O * 2^32 with E, O >= 0
+    // held in `even` / `odd` (8 words each).  One step for multiplier word y:
+    //   T <- (T + a*y + m*p) / 2^32,  m = (T + a*y) * INV mod 2^32.
+    // Even-indexed limbs of a and p multiply into the low-aligned accumulator, odd-indexed limbs
+    // into the one offset by a word.  After adding m*p the low-aligned accumulator has word 0 == 0;
+    // dropping that word makes it the offset accumulator of the next step (row_shift_mad), so the
+    // two arrays trade roles each step.  Carries out of the low-aligned accumulator (weight 2^256)
+    // are exactly one unit of word 7 of the offset accumulator.  The offset accumulator cannot
+    // overflow: T + a*y + m*p < (2 + 2^33) p < 2^288 for every p < 0.49 * 2^256.
+    HD Fe mul(const Fe& a, const Fe& b) const {
+        uint32_t even[8], odd[8];
+        // step 0
+        row_mul(even, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+        row_mul(odd, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+        {
+            uint32_t m = even[0] * F::INV;
+            row_mad_nocarry(odd, p[1], p[3], p[5], p[7], m);
+            row_mad(even, p[0], p[2], p[4], p[6], m, odd[7]);
+        }
+#pragma unroll
+        for (int i = 1; i < 8; i += 2) {
+            {  // odd step: `odd` is low-aligned, `even` is shifted
+                row_shift_mad(odd, even, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+                row_mad(odd, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], even[7]);
+                uint32_t m = odd[0] * F::INV;
+                row_mad_nocarry(even, p[1], p[3], p[5], p[7], m);
+                row_mad(odd, p[0], p[2], p[4], p[6], m, even[7]);
+            }
+            if (i + 1 < 8) {  // even step: roles back
+                row_shift_mad(even, odd, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+                row_mad(even, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], odd[7]);
+                uint32_t m = even[0] * F::INV;
+                row_mad_nocarry(odd, p[1], p[3], p[5], p[7], m);
+                row_mad(even, p[0], p[2], p[4], p[6], m, odd[7]);
+            }
+        }
+        // after step 7: low-aligned = odd (word 0 == 0), offset = even.  T = (odd >> 32) + even.
+        Fe r;
+        uint32_t hi[8];
+#pragma unroll
+        for (int i = 0; i < 7; i++) hi[i] = odd[i + 1];
+        hi[7] = 0;
+        add256(r.v, even, hi);  // T < 2p < 2^256
+        reduce_once(r.v);
+        return r;
+    }
+
+    HD Fe sqr(const Fe& a) const { return mul(a, a); }
+
+    // plain integer (< p) -> Montgomery (ff_ce from_repr) and back (into_repr)
+    HD Fe to_mont(const Fe& a) const { return mul(a, r2()); }
+    HD Fe from_mont(const Fe& a) const {
+        Fe o = zero();
+        o.v[0] = 1;
+        return mul(a, o);
+    }
+
+    HD Fe pow(const Fe& base, uint64_t e) const {
+        Fe acc = one(), b = base;
+        while (e) {
+            if (e & 1) acc = mul(acc, b);
+            b = mul(b, b);
+            e >>= 1;
+        }
+        return acc;
+    }
+
+    HD static bool eq(const Fe& a, const Fe& b) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= a.v[i] ^ b.v[i];
+        return d == 0;
+    }
+    HD bool is_canonical(const Fe& a) const {
+        uint32_t u[8];
+        return sub256(u, a.v, p) != 0;  // a < p  <=>  a - p borrows
+    }
+};
+
+}  // namespace hodor

@@ -1,0 +1,567 @@
+// Host launchers, templated on the field.  Included by field_bls.cu / field_bn254.cu /
+// field_stark.cu, each of which instantiates one FieldOps table.
+#pragma once
+#include <cstring>
+#include <string>
+
+#include "context.h"
+#include "fri.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+namespace hodor {
+
+template <class F>
+struct Ops {
+    using Fld = Field<F>;
+
+    // ------------------------------------------------------------------ host scalars
+    static void h_mul(const Fe& a, const Fe& b, Fe& o) { o = Fld().mul(a, b); }
+    static void h_add(const Fe& a, const Fe& b, Fe& o) { o = Fld().add(a, b); }
+    static void h_sub(const Fe& a, const Fe& b, Fe& o) { o = Fld().sub(a, b); }
+    static void h_pow(const Fe& a, uint64_t e, Fe& o) { o = Fld().pow(a, e); }
+    static Fe pow2k(Fe a, uint32_t k) {  // a^(2^k)
+        Fld f;
+        for (uint32_t i = 0; i < k; i++) a = f.mul(a, a);
+        return a;
+    }
+    static int h_inverse(const Fe& a, Fe& o) {  // a^(p-2)
+        Fld f;
+        if (Fld::eq(a, Fld::zero())) return HODOR_ERR_INVALID_ARG;
+        uint32_t e[8];
+        for (int i = 0; i < 8; i++) e[i] = F::P(i);
+        for (uint32_t borrow = 2, i = 0; borrow && i < 8; i++) {  // e = p - 2
+            const uint32_t old = e[i];
+            e[i] = old - borrow;
+            borrow = old < borrow ? 1u : 0u;
+        }
+        Fe acc = Fld::one();
+        for (int i = 255; i >= 0; i--) {
+            acc = f.mul(acc, acc);
+            if ((e[i / 32] >> (i % 32)) & 1) acc = f.mul(acc, a);
+        }
+        o = acc;
+        return HODOR_OK;
+    }
+    static void h_from_repr(const Fe& a, Fe& o) { o = Fld().to_mont(a); }
+    static void h_into_repr(const Fe& a, Fe& o) { o = Fld().from_mont(a); }
+    static Fe from_u64(uint64_t x) {
+        Fe t = Fld::zero();
+        t.v[0] = (uint32_t)x;
+        t.v[1] = (uint32_t)(x >> 32);
+        return Fld().to_mont(t);
+    }
+    static Fe generator() { return from_u64(F::GENERATOR); }
+    static Fe root_of_unity() {  // generator^((p-1) >> S), ff_ce derive
+        Fld f;
+        uint32_t e[8];
+        for (int i = 0; i < 8; i++) e[i] = F::P(i);
+        e[0] -= 1;
+        for (int s = 0; s < F::S; s++) {
+            for (int i = 0; i < 7; i++) e[i] = (e[i] >> 1) | (e[i + 1] << 31);
+            e[7] >>= 1;
+        }
+        const Fe g = generator();
+        Fe acc = Fld::one();
+        for (int i = 255; i >= 0; i--) {
+            acc = f.mul(acc, acc);
+            if ((e[i / 32] >> (i % 32)) & 1) acc = f.mul(acc, g);
+        }
+        return acc;
+    }
+    static void h_constants(Fe& modulus, Fe& one, Fe& gen, Fe& root, uint32_t& s, uint32_t& num_bits) {
+        for (int i = 0; i < 8; i++) modulus.v[i] = F::P(i);
+        one = Fld::one();
+        gen = generator();
+        root = root_of_unity();
+        s = F::S;
+        num_bits = F::NUM_BITS;
+    }
+    static int h_domain_generator(uint32_t log_n, Fe& out) {
+        if (log_n > (uint32_t)F::S) return HODOR_ERR_DOMAIN;
+        static const Fe root = root_of_unity();
+        out = pow2k(root, F::S - log_n);
+        return HODOR_OK;
+    }
+    static int h_root_to_challenge(const uint8_t* d, Fe& out) {
+        Fe v;
+        for (int j = 0; j < 8; j++)
+            v.v[7 - j] = ((uint32_t)d[4 * j] << 24) | ((uint32_t)d[4 * j + 1] << 16) | ((uint32_t)d[4 * j + 2] << 8) |
+                         (uint32_t)d[4 * j + 3];
+        constexpr uint32_t shave = (256 - (F::NUM_BITS - 1)) % 64;
+        if (shave >= 32) {
+            v.v[7] = 0;
+            v.v[6] &= 0xffffffffu >> (shave - 32);
+        } else {
+            v.v[7] &= 0xffffffffu >> shave;
+        }
+        Fld f;
+        if (!f.is_canonical(v)) return HODOR_ERR_INVALID_ARG;  // reference: expect("in a field") panics
+        out = f.to_mont(v);
+        return HODOR_OK;
+    }
+
+    // ------------------------------------------------------------------ tables
+    static std::string key_of(const char* tag, uint32_t a, uint32_t b, const Fe* elems, int n_elems) {
+        std::string k(tag);
+        k.push_back((char)F::ID);
+        k.append((const char*)&a, 4);
+        k.append((const char*)&b, 4);
+        for (int i = 0; i < n_elems; i++) k.append((const char*)elems[i].v, 32);
+        return k;
+    }
+
+    // tables of bases[b]^e, e in [0, 2^bits); `scale` (optional) is folded into the lo tables
+    static int build_pow_tables(Ctx& c, PowTables& t, const std::vector<Fe>& bases, uint32_t bits, const Fe* scale,
+                                cudaStream_t st) {
+        const uint32_t nb = (uint32_t)bases.size();
+        t.count = nb;
+        t.lo_bits = (bits + 1) / 2;
+        t.hi_bits = bits - t.lo_bits;
+        const size_t lo_n = (size_t)nb << t.lo_bits, hi_n = (size_t)nb << t.hi_bits;
+        const size_t hdr = 2 * (size_t)nb + 1;  // Fe slots: lo bases, hi bases, scale
+        t.bytes = (hdr + lo_n + hi_n) * sizeof(Fe);
+        HODOR_CUDA_TRY(cudaMalloc((void**)&t.block, t.bytes));
+        std::vector<Fe> h(hdr);
+        for (uint32_t i = 0; i < nb; i++) {
+            h[i] = bases[i];
+            h[nb + i] = pow2k(bases[i], t.lo_bits);
+        }
+        h[2 * nb] = scale ? *scale : Fld::one();
+        HODOR_CUDA_TRY(cudaMemcpyAsync(t.block, h.data(), hdr * sizeof(Fe), cudaMemcpyHostToDevice, st));
+        HODOR_CUDA_TRY(cudaStreamSynchronize(st));  // h is a stack-owned vector
+        const Fe* d_hdr = (const Fe*)t.block;
+        t.lo = t.block + 2 * hdr;
+        t.hi = t.lo + 2 * lo_n;
+        {
+            const uint32_t cnt = 1u << t.lo_bits;
+            dim3 grid((cnt + 255) / 256, nb);
+            ProfScope ps(c, st, "pow_table");
+            pow_table_kernel<F><<<grid, 256, 0, st>>>(t.lo, d_hdr, scale ? d_hdr + 2 * nb : nullptr, cnt, 0u);
+        }
+        {
+            const uint32_t cnt = 1u << t.hi_bits;
+            dim3 grid((cnt + 255) / 256, nb);
+            ProfScope ps(c, st, "pow_table");
+            pow_table_kernel<F><<<grid, 256, 0, st>>>(t.hi, d_hdr + nb, nullptr, cnt, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        HODOR_CUDA_TRY(cudaStreamSynchronize(st));  // tables may be used from other streams later
+        c.table_bytes += t.bytes;
+        return HODOR_OK;
+    }
+
+    // Tables are small (a few MiB each) but the cache is kept bounded.  Only called at the top of an
+    // entry point, before any table pointer has been fetched, and after a device-wide sync.
+    static void maybe_evict(Ctx& c) {
+        if (c.pow_tables.size() <= 64 && c.ntt_tables.size() <= 32) return;
+        cudaDeviceSynchronize();
+        for (auto& kv : c.pow_tables) cudaFree(kv.second.block);
+        for (auto& kv : c.ntt_tables) {
+            cudaFree(kv.second.pw.block);
+            cudaFree(kv.second.tw_b_block);
+        }
+        c.pow_tables.clear();
+        c.ntt_tables.clear();
+        c.table_bytes = 0;
+    }
+
+    static int get_pow_tables(Ctx& c, const PowTables** out, const std::vector<Fe>& bases, uint32_t bits, const Fe* scale,
+                              cudaStream_t st) {
+        std::vector<Fe> k(bases);
+        if (scale) k.push_back(*scale);
+        const std::string key = key_of("pow", bits, scale ? 1 : 0, k.data(), (int)k.size());
+        auto it = c.pow_tables.find(key);
+        if (it == c.pow_tables.end()) {
+            PowTables t;
+            int rc = build_pow_tables(c, t, bases, bits, scale, st);
+            if (rc) return rc;
+            it = c.pow_tables.emplace(key, t).first;
+        }
+        *out = &it->second;
+        return HODOR_OK;
+    }
+
+    static int get_ntt_tables(Ctx& c, const NttTables** out, uint32_t log_n, const Fe& omega, cudaStream_t st) {
+        const std::string key = key_of("ntt", log_n, 0, &omega, 1);
+        auto it = c.ntt_tables.find(key);
+        if (it == c.ntt_tables.end()) {
+            NttTables t;
+            std::vector<Fe> base{omega};
+            int rc = build_pow_tables(c, t.pw, base, log_n == 0 ? 1 : log_n, nullptr, st);
+            if (rc) return rc;
+            if (log_n >= 4) {
+                Fld f;
+                const Fe w16 = pow2k(omega, log_n - 4);
+                Fe acc = w16;
+                for (int k = 0; k < 7; k++) {
+                    t.wr[k] = acc;
+                    acc = f.mul(acc, w16);
+                }
+            }
+            const NttPlan plan = make_plan(log_n);
+            if (plan.passes) {
+                size_t total = 0;
+                bool need[10] = {};
+                for (int i = 0; i < plan.passes; i++) need[plan.b[i]] = true;
+                for (int b = 6; b <= 9; b++)
+                    if (need[b]) total += (size_t)1 << b;
+                t.bytes = total * sizeof(Fe);
+                HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_b_block, t.bytes));
+                Fe* d_base = nullptr;  // device copy of the per-B bases
+                HODOR_CUDA_TRY(cudaMalloc((void**)&d_base, 4 * sizeof(Fe)));
+                uint4* cur = t.tw_b_block;
+                Fe hb[4];
+                int nb = 0;
+                for (int b = 6; b <= 9; b++)
+                    if (need[b]) hb[nb++] = pow2k(omega, log_n - b);
+                HODOR_CUDA_TRY(cudaMemcpyAsync(d_base, hb, nb * sizeof(Fe), cudaMemcpyHostToDevice, st));
+                nb = 0;
+                for (int b = 6; b <= 9; b++) {
+                    if (!need[b]) continue;
+                    t.tw_b[b] = cur;
+                    const uint32_t cnt = 1u << b;
+                    {
+                        ProfScope ps(c, st, "pow_table");
+                        pow_table_kernel<F><<<dim3((cnt + 255) / 256, 1), 256, 0, st>>>(cur, d_base + nb, nullptr, cnt, 0u);
+                    }
+                    cur += 2 * (size_t)cnt;
+                    nb++;
+                }
+                HODOR_CUDA_TRY(cudaGetLastError());
+                HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                cudaFree(d_base);
+                c.table_bytes += t.bytes;
+            }
+            it = c.ntt_tables.emplace(key, t).first;
+        }
+        *out = &it->second;
+        return HODOR_OK;
+    }
+
+    // ------------------------------------------------------------------ transforms
+    template <int B, bool SCALE_IN, bool LAST>
+    static int launch_pass(Ctx& c, const NttPass& p, dim3 grid, cudaStream_t st) {
+        auto kern = ntt_pass_kernel<F, B, SCALE_IN, LAST>;
+        constexpr size_t smem = (size_t)256 << B;
+        static bool configured = false;  // guarded by Ctx::mu
+        if (!configured) {
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        {
+            ProfScope ps(c, st, LAST ? "ntt_pass_last" : (SCALE_IN ? "ntt_pass_first_scaled" : "ntt_pass"));
+            kern<<<grid, 1 << B, smem, st>>>(p);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+    template <bool SCALE_IN, bool LAST>
+    static int launch_pass_b(Ctx& c, int b, const NttPass& p, dim3 grid, cudaStream_t st) {
+        switch (b) {
+            case 6: return launch_pass<6, SCALE_IN, LAST>(c, p, grid, st);
+            case 7: return launch_pass<7, SCALE_IN, LAST>(c, p, grid, st);
+            case 8: return launch_pass<8, SCALE_IN, LAST>(c, p, grid, st);
+            case 9: return launch_pass<9, SCALE_IN, LAST>(c, p, grid, st);
+        }
+        return fail(HODOR_ERR_INVALID_ARG, "internal: bad pass width");
+    }
+
+    static int ntt(Ctx& c, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_l, const Fe& omega,
+                   const Fe* shift0, const Fe* step, int out_mode, const Fe* out_g, cudaStream_t st) {
+        Fld f;
+        if (log_n > 32 || log_n + log_l > 34) return fail(HODOR_ERR_INVALID_ARG, "transform too large");
+        maybe_evict(c);
+        // omega must be a primitive 2^log_n-th root: omega^(n/2) == -1  (n == 1: omega == 1)
+        {
+            const Fe minus_one = f.neg(Fld::one());
+            const Fe h = log_n ? pow2k(omega, log_n - 1) : omega;
+            if (!Fld::eq(h, log_n ? minus_one : Fld::one()))
+                return fail(HODOR_ERR_NOT_A_ROOT, "omega is not a primitive 2^log_n-th root of unity");
+        }
+        const size_t n = (size_t)1 << log_n;
+        const uint32_t L = 1u << log_l;
+        const NttTables* tw = nullptr;
+        int rc = get_ntt_tables(c, &tw, log_n, omega, st);
+        if (rc) return rc;
+
+        const PowTables* coset = nullptr;
+        if (shift0 != nullptr) {
+            std::vector<Fe> bases(L);
+            Fe cur = *shift0;
+            for (uint32_t i = 0; i < L; i++) {
+                bases[i] = cur;
+                if (step) cur = f.mul(cur, *step);
+            }
+            rc = get_pow_tables(c, &coset, bases, log_n == 0 ? 1 : log_n, nullptr, st);
+            if (rc) return rc;
+        } else if (log_l != 0) {
+            return fail(HODOR_ERR_INVALID_ARG, "internal: cosets without shifts");
+        }
+
+        uint32_t flags = 0;
+        Fe out_const = Fld::zero();
+        const PowTables* out_pow = nullptr;
+        if (out_mode) {
+            Fe ninv;
+            h_inverse(from_u64((uint64_t)n), ninv);
+            if (out_mode == 1) {
+                flags |= PASS_OUT_CONST;
+                out_const = ninv;
+            } else {
+                std::vector<Fe> bases{*out_g};
+                rc = get_pow_tables(c, &out_pow, bases, log_n == 0 ? 1 : log_n, out_mode == 3 ? nullptr : &ninv, st);
+                if (rc) return rc;
+                flags |= PASS_OUT_POW;
+            }
+        }
+
+        const NttPlan plan = make_plan(log_n);
+        if (plan.passes == 0) {
+            SmallNtt p{};
+            p.in = in;
+            p.out = out;
+            p.log_n = log_n;
+            p.log_l = log_l;
+            p.flags = flags;
+            p.zero = 0;
+            p.out_const = out_const;
+            if (out_pow) p.out_pow = out_pow->two_level();
+            if (coset) {
+                p.coset = coset->two_level();
+                p.coset_stride_lo = coset->stride_lo();
+                p.coset_stride_hi = coset->stride_hi();
+            }
+            // the single-block kernel wants omega^e directly, e < n/2: a dedicated flat table
+            const PowTables* flat = nullptr;
+            {
+                const std::string key = key_of("flat", log_n, 0, &omega, 1);
+                auto it = c.pow_tables.find(key);
+                if (it == c.pow_tables.end()) {
+                    PowTables t;
+                    t.count = 1;
+                    t.lo_bits = log_n;
+                    t.bytes = (n + 1) * sizeof(Fe);
+                    HODOR_CUDA_TRY(cudaMalloc((void**)&t.block, t.bytes));
+                    HODOR_CUDA_TRY(cudaMemcpyAsync(t.block, &omega, sizeof(Fe), cudaMemcpyHostToDevice, st));
+                    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                    t.lo = t.block + 2;
+                    {
+                        ProfScope ps(c, st, "pow_table");
+                        pow_table_kernel<F><<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, st>>>(
+                            t.lo, (const Fe*)t.block, nullptr, (uint32_t)n, 0u);
+                    }
+                    HODOR_CUDA_TRY(cudaGetLastError());
+                    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                    c.table_bytes += t.bytes;
+                    it = c.pow_tables.emplace(key, t).first;
+                }
+                flat = &it->second;
+            }
+            p.tw = flat->lo;
+            auto kern = ntt_small_kernel<F>;
+            const size_t smem = n * sizeof(Fe);
+            static bool configured = false;
+            if (!configured) {
+                HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32));
+                configured = true;
+            }
+            unsigned threads = (unsigned)(n / 2 < 32 ? 32 : (n / 2 > 1024 ? 1024 : n / 2));
+            {
+                ProfScope ps(c, st, "ntt_small");
+                kern<<<L, threads, smem, st>>>(p);
+            }
+            HODOR_CUDA_TRY(cudaGetLastError());
+            return HODOR_OK;
+        }
+
+        // ---- multi-pass ----
+        rc = c.ensure_workspace(n * L * sizeof(Fe));
+        if (rc) return rc;
+        uint4* work = (uint4*)c.ws;
+        NttPass p{};
+        p.log_n = log_n;
+        p.log_l = log_l;
+        p.b1 = plan.b[0];
+        p.zero = 0;
+        p.tw = tw->pw.two_level();
+        p.out_const = out_const;
+        if (out_pow) p.out_pow = out_pow->two_level();
+        if (coset) {
+            p.coset = coset->two_level();
+            p.coset_stride_lo = coset->stride_lo();
+            p.coset_stride_hi = coset->stride_hi();
+        }
+        for (int k = 0; k < 7; k++) p.wr[k] = tw->wr[k];
+        uint32_t below = log_n;
+        for (int i = 0; i < plan.passes; i++) {
+            const int b = plan.b[i];
+            below -= b;
+            const bool last = (i == plan.passes - 1);
+            p.s = below;
+            p.tw_b = tw->tw_b[b];
+            p.tw_shift = log_n - below - b;
+            p.flags = last ? flags : 0;
+            if (!last) {
+                p.in = (i == 0) ? in : work;
+                p.out = work;
+                dim3 grid((unsigned)(n >> (b + 3)), L);
+                if (i == 0 && coset) rc = launch_pass_b<true, false>(c, b, p, grid, st);
+                else rc = launch_pass_b<false, false>(c, b, p, grid, st);
+            } else {
+                p.in = work;
+                p.out = out;
+                p.mid0 = plan.passes >= 3 ? plan.b[1] : 0;
+                p.mid1 = plan.passes >= 4 ? plan.b[2] : 0;
+                if (plan.passes == 3) p.mid1 = 0;
+                dim3 grid((unsigned)(((size_t)L << log_n) >> (b + 3)), 1);
+                rc = launch_pass_b<false, true>(c, b, p, grid, st);
+            }
+            if (rc) return rc;
+        }
+        return HODOR_OK;
+    }
+
+    static int scale_pow(Ctx& c, uint4* a, size_t n, const Fe& g, cudaStream_t st) {
+        maybe_evict(c);
+        uint32_t bits = 1;
+        while (((size_t)1 << bits) < n) bits++;
+        const PowTables* t = nullptr;
+        std::vector<Fe> bases{g};
+        int rc = get_pow_tables(c, &t, bases, bits, nullptr, st);
+        if (rc) return rc;
+        const unsigned grid = (unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+        {
+            ProfScope ps(c, st, "scale_pow");
+            scale_pow_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(a, n, t->two_level(), 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
+    static int elementwise(Ctx& c, int op, const uint4* a, const uint4* b, uint4* out, size_t n, cudaStream_t st) {
+        if (op < 0 || op > 3) return fail(HODOR_ERR_INVALID_ARG, "unknown elementwise op");
+        const unsigned grid = (unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+        {
+            ProfScope ps(c, st, "elementwise");
+            elementwise_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(op, a, b, out, n, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
+    // ------------------------------------------------------------------ Merkle tail, FRI fold
+    static int merkle_tail(Ctx& c, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
+                           cudaStream_t st) {
+        unsigned threads = w_in / 2 < 32 ? 32 : (w_in / 2 > 1024 ? 1024 : w_in / 2);
+        {
+            ProfScope ps(c, st, "merkle_tail");
+            if (leaf) merkle_tail_kernel<F, true><<<1, threads, 0, st>>>(in, nodes, w_in, c.key, root, chal, 0u);
+            else merkle_tail_kernel<F, false><<<1, threads, 0, st>>>(in, nodes, w_in, c.key, root, chal, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
+    static int fri_fold(Ctx& c, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
+                        cudaStream_t st) {
+        // omega_N^-1 of the INITIAL domain (src/fri/fri_on_values.rs:24-25), table over exponents < N/2
+        maybe_evict(c);
+        Fe omega, omega_inv;
+        int rc = h_domain_generator(log_n0, omega);
+        if (rc) return fail(rc, "FRI domain larger than the field's 2-adicity");
+        h_inverse(omega, omega_inv);
+        const PowTables* t = nullptr;
+        std::vector<Fe> bases{omega_inv};
+        rc = get_pow_tables(c, &t, bases, log_n0 > 1 ? log_n0 - 1 : 1, nullptr, st);
+        if (rc) return rc;
+        const size_t half = n / 2;
+        const unsigned grid = (unsigned)((half + 255) / 256 > 148 * 16 ? 148 * 16 : (half + 255) / 256);
+        {
+            ProfScope ps(c, st, "fri_fold");
+            fri_fold_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), layer, chal, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
+    static int shard_rows(Ctx& c, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_g, uint32_t rank,
+                          const Fe& omega, cudaStream_t st);
+
+    static FieldOps table() {
+        FieldOps o;
+        o.h_mul = h_mul;
+        o.h_add = h_add;
+        o.h_sub = h_sub;
+        o.h_pow = h_pow;
+        o.h_inverse = h_inverse;
+        o.h_from_repr = h_from_repr;
+        o.h_into_repr = h_into_repr;
+        o.h_constants = h_constants;
+        o.h_domain_generator = h_domain_generator;
+        o.h_root_to_challenge = h_root_to_challenge;
+        o.ntt = ntt;
+        o.scale_pow = scale_pow;
+        o.elementwise = elementwise;
+        o.merkle_tail = merkle_tail;
+        o.fri_fold = fri_fold;
+        o.shard_rows = shard_rows;
+        return o;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Four-step across G GPUs, step B: after the all-to-all rank h holds M[g][k] = B_g[h*m/G + k],
+// g < G, k < m/G (m = n/G); it computes, for every k, the G-point DFT over g:
+//   out[k2 * (m/G) + k] = sum_g M[g][k] * omega_G^(g*k2)          = A[(h*m/G + k) + m*k2]
+// ---------------------------------------------------------------------------------------------
+template <class F, int LOGG>
+__global__ void __launch_bounds__(256) shard_rows_kernel(const uint4* in, uint4* out, size_t cols,
+                                                         const __grid_constant__ NttPass p) {
+    const uint32_t oz = threadIdx.x & p.zero;
+    const Field<F> fld(oz);
+    constexpr int G = 1 << LOGG;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < cols; k += (size_t)gridDim.x * blockDim.x) {
+        Fe x[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) x[g] = ld_fe(in, (size_t)g * cols + k);
+        if constexpr (LOGG > 0) dif_inreg<F, LOGG>(fld, x, p, oz);
+#pragma unroll
+        for (int k2 = 0; k2 < G; k2++) st_fe(out, (size_t)k2 * cols + k, x[bitrev_c(k2, LOGG)]);
+    }
+}
+
+template <class F>
+int Ops<F>::shard_rows(Ctx& c, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_g, uint32_t rank,
+                       const Fe& omega, cudaStream_t st) {
+    (void)rank;
+    if (log_g > 4 || log_n < 2 * log_g) return fail(HODOR_ERR_INVALID_ARG, "shard_rows: need log_g <= 4 and log_n >= 2*log_g");
+    Fld f;
+    NttPass p{};
+    p.zero = 0;
+    // dif_inreg expects wr[k-1] = w16^k where w16^(16/R) is the radix-R root; here R = G and the
+    // root is omega_G = omega^(n/G): set w16 = omega^(n/16) (exists when log_n >= 4)
+    if (log_g > 0) {
+        if (log_n < 4) return fail(HODOR_ERR_INVALID_ARG, "shard_rows: log_n < 4");
+        const Fe w16 = pow2k(omega, log_n - 4);
+        Fe acc = w16;
+        for (int k = 0; k < 7; k++) {
+            p.wr[k] = acc;
+            acc = f.mul(acc, w16);
+        }
+    }
+    const size_t cols = ((size_t)1 << log_n) >> (2 * log_g);
+    const unsigned grid = (unsigned)((cols + 255) / 256 > 148 * 8 ? 148 * 8 : (cols + 255) / 256);
+    ProfScope ps(c, st, "shard_rows");
+    switch (log_g) {
+        case 0: shard_rows_kernel<F, 0><<<grid ? grid : 1, 256, 0, st>>>(in, out, cols, p); break;
+        case 1: shard_rows_kernel<F, 1><<<grid ? grid : 1, 256, 0, st>>>(in, out, cols, p); break;
+        case 2: shard_rows_kernel<F, 2><<<grid ? grid : 1, 256, 0, st>>>(in, out, cols, p); break;
+        case 3: shard_rows_kernel<F, 3><<<grid ? grid : 1, 256, 0, st>>>(in, out, cols, p); break;
+        case 4: shard_rows_kernel<F, 4><<<grid ? grid : 1, 256, 0, st>>>(in, out, cols, p); break;
+    }
+    HODOR_CUDA_TRY(cudaGetLastError());
+    return HODOR_OK;
+}
+
+}  // namespace hodor

@@ -1,0 +1,33 @@
+// FRI fold for sm_100a: one layer of NaiveFriIop::proof_from_lde_by_values,
+// src/fri/fri_on_values.rs:61-101.
+//
+//   next[idx] = ((v[idx] + v[idx+M/2]) + c * (v[idx] - v[idx+M/2]) * omega_N^(-idx * 2^layer)) * 2^-1
+//
+// The reference reads omega_N^-e from a precomputed N/2-entry table (:24-40) and multiplies by a
+// precomputed 2^-1; here the power comes from a two-level table (2 * sqrt(N) entries, L2 resident)
+// and the halving is a shift with a conditional add of p (exact, because halving is linear and so
+// commutes with the Montgomery factor).  The challenge c is read from device memory, where the
+// Merkle tail kernel of the previous layer left it, so the whole commit chain runs without a host
+// round trip.
+#pragma once
+#include "field.cuh"
+#include "ntt.cuh"
+
+namespace hodor {
+
+template <class F>
+__global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* out, size_t half, TwoLevel winv,
+                                                       uint32_t layer, const uint4* challenge, uint32_t zero) {
+    const Field<F> fld(threadIdx.x & zero);
+    const Fe c = ld_fe(challenge, 0);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < half; idx += (size_t)gridDim.x * blockDim.x) {
+        const Fe f0 = ld_fe(in, idx), f1 = ld_fe(in, idx + half);
+        const Fe even = fld.add(f0, f1);
+        Fe odd = fld.sub(f0, f1);
+        odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, (uint64_t)idx << layer));
+        odd = fld.mul(odd, c);
+        st_fe(out, idx, fld.halve(fld.add(odd, even)));
+    }
+}
+
+}  // namespace hodor

@@ -1,0 +1,230 @@
+// Keyed, personalised Blake2s-256 Merkle tree (the IOP oracle) for sm_100a.
+//
+// Replaces Blake2sIopTree::create, src/iop/blake2s_trivial_iop.rs:131-219, with the hashing of
+// :8-16 (parameters), :36-42 (leaf = raw little-endian Montgomery limbs, 32 B), :81-104
+// (hash_leaf / hash_node) and the root -> challenge map of :48-60.
+//
+// On the CPU every hash is two compressions (key block, then data block).  The key-block
+// compression does not depend on the data, so its output chaining value is computed once on the
+// host and every device hash is a single compression that starts from it.
+//
+// Node layout is the reference's: one array of n 32-byte digests in heap order, nodes[0] unused
+// (zero), nodes[1] the root, the level with w nodes at [w, 2w), the bottom node level at [n/2, n)
+// built from pairs of leaf hashes (which are not stored).
+#pragma once
+#include <cuda_runtime.h>
+#include "field.cuh"
+#include "ntt.cuh"
+
+namespace hodor {
+
+struct B2sState {
+    uint32_t h[8];
+};
+
+HD constexpr uint32_t b2s_iv(int i) {
+    constexpr uint32_t iv[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au,
+                                0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    return iv[i];
+}
+HD constexpr int b2s_sigma(int r, int i) {
+    constexpr unsigned char s[10][16] = {
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+        {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+        {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+        {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+        {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+    return s[r][i];
+}
+
+HD uint32_t rotr32(uint32_t x, int r) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(x, x, r);
+#else
+    return (x >> r) | (x << (32 - r));
+#endif
+}
+
+#define HODOR_B2S_G(a, b, c, d, x, y) \
+    v[a] = v[a] + v[b] + (x);         \
+    v[d] = rotr32(v[d] ^ v[a], 16);   \
+    v[c] = v[c] + v[d];               \
+    v[b] = rotr32(v[b] ^ v[c], 12);   \
+    v[a] = v[a] + v[b] + (y);         \
+    v[d] = rotr32(v[d] ^ v[a], 8);    \
+    v[c] = v[c] + v[d];               \
+    v[b] = rotr32(v[b] ^ v[c], 7);
+
+// One Blake2s compression (RFC 7693 3.2).  m[] indices are compile-time after unrolling, so the
+// message stays in registers; with HALF only m[0..7] are non-zero (32-byte leaf message).
+template <bool HALF>
+HD void b2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint32_t t0, bool last) {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[i] = h[i];
+        v[i + 8] = b2s_iv(i);
+    }
+    v[12] ^= t0;
+    if (last) v[14] = ~v[14];
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#define MSG(i) ((HALF && b2s_sigma(r, i) >= 8) ? 0u : m[b2s_sigma(r, i)])
+        HODOR_B2S_G(0, 4, 8, 12, MSG(0), MSG(1))
+        HODOR_B2S_G(1, 5, 9, 13, MSG(2), MSG(3))
+        HODOR_B2S_G(2, 6, 10, 14, MSG(4), MSG(5))
+        HODOR_B2S_G(3, 7, 11, 15, MSG(6), MSG(7))
+        HODOR_B2S_G(0, 5, 10, 15, MSG(8), MSG(9))
+        HODOR_B2S_G(1, 6, 11, 12, MSG(10), MSG(11))
+        HODOR_B2S_G(2, 7, 8, 13, MSG(12), MSG(13))
+        HODOR_B2S_G(3, 4, 9, 14, MSG(14), MSG(15))
+#undef MSG
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+
+// Chaining value after the key block of BASE_BLAKE2S_PARAMS (src/iop/blake2s_trivial_iop.rs:8-16):
+// digest 32, key "Squeamish Ossifrage" (19 B), fanout 1, depth 1, personal "Shaftoe".
+inline B2sState b2s_keyed_state() {
+    B2sState s;
+    const char key[] = "Squeamish Ossifrage";
+    const char personal[8] = {'S', 'h', 'a', 'f', 't', 'o', 'e', 0};
+    for (int i = 0; i < 8; i++) s.h[i] = b2s_iv(i);
+    s.h[0] ^= 0x01010000u ^ (19u << 8) ^ 32u;
+    uint32_t pw[2] = {0, 0};
+    for (int i = 0; i < 8; i++) pw[i / 4] |= (uint32_t)(unsigned char)personal[i] << (8 * (i % 4));
+    s.h[6] ^= pw[0];
+    s.h[7] ^= pw[1];
+    uint32_t m[16] = {0};
+    for (int i = 0; i < 19; i++) m[i / 4] |= (uint32_t)(unsigned char)key[i] << (8 * (i % 4));
+    b2s_compress<false>(s.h, m, 64u, false);
+    return s;
+}
+
+struct Digest {
+    uint32_t w[8];
+};
+
+// hash_leaf: message = 32 raw bytes, total input 64 (key block) + 32
+HD Digest hash_leaf32(const B2sState& key, const uint32_t (&leaf)[8]) {
+    uint32_t h[8], m[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        h[i] = key.h[i];
+        m[i] = leaf[i];
+        m[i + 8] = 0;
+    }
+    b2s_compress<true>(h, m, 96u, true);
+    Digest d;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d.w[i] = h[i];
+    return d;
+}
+// hash_node: message = left || right, total input 64 + 64
+HD Digest hash_node64(const B2sState& key, const Digest& l, const Digest& r) {
+    uint32_t h[8], m[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        h[i] = key.h[i];
+        m[i] = l.w[i];
+        m[i + 8] = r.w[i];
+    }
+    b2s_compress<false>(h, m, 128u, true);
+    Digest d;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d.w[i] = h[i];
+    return d;
+}
+
+DEV Digest ld_digest(const uint4* base, size_t idx) {
+    const uint4 a = base[2 * idx], b = base[2 * idx + 1];
+    Digest d;
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
+    d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    return d;
+}
+DEV void st_digest(uint4* base, size_t idx, const Digest& d) {
+    base[2 * idx] = make_uint4(d.w[0], d.w[1], d.w[2], d.w[3]);
+    base[2 * idx + 1] = make_uint4(d.w[4], d.w[5], d.w[6], d.w[7]);
+}
+
+// Thread-serial subtree over 2^K consecutive inputs starting at input index `first`.
+// Inputs are leaves (LEAF) or the digests of the level with `w_in` nodes.  The node covering
+// inputs [a*2^j, (a+1)*2^j) lives at heap index (w_in >> j) + a.
+template <int K, bool LEAF>
+DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, size_t w_in, size_t first) {
+    if constexpr (K == 0) {
+        const Digest raw = ld_digest(in, first);
+        if constexpr (LEAF) return hash_leaf32(key, raw.w);
+        else return raw;
+    } else {
+        const Digest l = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first);
+        const Digest r = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first + ((size_t)1 << (K - 1)));
+        const Digest d = hash_node64(key, l, r);
+        st_digest(nodes, (w_in >> K) + (first >> K), d);
+        return d;
+    }
+}
+
+// grid-stride over groups of 2^K inputs; writes K node levels
+template <int K, bool LEAF>
+__global__ void __launch_bounds__(256) merkle_levels_kernel(const uint4* in, uint4* nodes, size_t w_in,
+                                                            const __grid_constant__ B2sState key) {
+    const size_t groups = w_in >> K;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x)
+        merkle_subtree<K, LEAF>(key, in, nodes, w_in, g << K);
+}
+
+// Finishes a tree inside one block: from `w_in` inputs (leaves if LEAF, else the stored level of
+// w_in nodes) up to the root, then root -> challenge (interpret_hash, :48-60) in Montgomery form.
+template <class F, bool LEAF>
+__global__ void __launch_bounds__(1024) merkle_tail_kernel(const uint4* in, uint4* nodes, uint32_t w_in,
+                                                           const __grid_constant__ B2sState key, uint4* root_out,
+                                                           uint4* challenge_out, uint32_t zero) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {  // nodes[0] is never written by the reference: stays [0u8; 32]
+        Digest z;
+#pragma unroll
+        for (int i = 0; i < 8; i++) z.w[i] = 0;
+        st_digest(nodes, 0, z);
+    }
+    uint32_t width = w_in / 2;
+    if constexpr (LEAF) {
+        for (uint32_t i = tid; i < width; i += nt) {
+            const Digest a = ld_digest(in, 2 * i), b = ld_digest(in, 2 * i + 1);
+            st_digest(nodes, width + i, hash_node64(key, hash_leaf32(key, a.w), hash_leaf32(key, b.w)));
+        }
+        __syncthreads();
+        width /= 2;
+    }
+    for (; width >= 1; width /= 2) {
+        for (uint32_t i = tid; i < width; i += nt) {
+            const Digest a = ld_digest(nodes, 2 * (size_t)(width + i)), b = ld_digest(nodes, 2 * (size_t)(width + i) + 1);
+            st_digest(nodes, width + i, hash_node64(key, a, b));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const Digest root = ld_digest(nodes, 1);
+        if (root_out != nullptr) st_digest(root_out, 0, root);
+        if (challenge_out != nullptr) {
+            // read_be: digest bytes are one big-endian 256-bit integer; word j (LE load) holds
+            // bytes 4j..4j+3, so limb (7 - j) = byteswap(word j)
+            Fe v;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v.v[7 - j] = __byte_perm(root.w[j], 0, 0x0123);
+            constexpr uint32_t shave = (256 - (F::NUM_BITS - 1)) % 64;  // 256 - CAPACITY
+            if constexpr (shave >= 32) {
+                v.v[7] = 0;
+                v.v[6] &= 0xffffffffu >> (shave - 32);
+            } else {
+                v.v[7] &= 0xffffffffu >> shave;
+            }
+            const Field<F> fld(tid & zero);
+            st_fe(challenge_out, 0, fld.to_mont(v));  // from_repr
+        }
+    }
+}
+
+}  // namespace hodor

@@ -1,0 +1,77 @@
+// Field-independent part of the Merkle build: the wide levels (thread-serial subtrees) and the
+// authentication-path gather.  Reference: Blake2sIopTree::create / get_path,
+// src/iop/blake2s_trivial_iop.rs:131-219, 251-279.
+#include "context.h"
+
+namespace hodor {
+
+static unsigned grid_for(size_t work_items, unsigned block) {
+    size_t g = (work_items + block - 1) / block;
+    const size_t cap = 148 * 16;
+    if (g > cap) g = cap;
+    return (unsigned)(g ? g : 1);
+}
+
+template <int K, bool LEAF>
+static int launch_levels(Ctx& c, const uint4* in, uint4* nodes, size_t w_in, cudaStream_t st) {
+    {
+        ProfScope ps(c, st, LEAF ? "merkle_levels_leaf" : "merkle_levels_node");
+        merkle_levels_kernel<K, LEAF><<<grid_for(w_in >> K, 256), 256, 0, st>>>(in, nodes, w_in, c.key);
+    }
+    HODOR_CUDA_TRY(cudaGetLastError());
+    return HODOR_OK;
+}
+
+// Hashes the wide part of the tree.  On return *remaining_width is the width (<= 4096) of the
+// lowest level that has been written; 0 means nothing was done (n <= 4096: the tail kernel takes
+// the leaves directly).
+int merkle_levels(Ctx& c, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st) {
+    *remaining_width = 0;
+    if (n <= 4096) return HODOR_OK;
+    int rc = launch_levels<3, true>(c, leaves, nodes, n, st);  // levels n/2, n/4, n/8
+    if (rc) return rc;
+    size_t w = n >> 3;
+    while (w > 4096) {
+        int k = 0;
+        while (k < 3 && (w >> (k + 1)) >= 4096) k++;  // land exactly on 4096 or above
+        if (k == 0) k = 1;
+        const uint4* in = nodes + 2 * w;
+        switch (k) {
+            case 1: rc = launch_levels<1, false>(c, in, nodes, w, st); break;
+            case 2: rc = launch_levels<2, false>(c, in, nodes, w, st); break;
+            default: rc = launch_levels<3, false>(c, in, nodes, w, st); break;
+        }
+        if (rc) return rc;
+        w >>= k;
+    }
+    *remaining_width = w;
+    return HODOR_OK;
+}
+
+// out[0] = hash_leaf(values[index ^ 1]); out[1 + j] = sibling on the way up
+__global__ void merkle_path_kernel(const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
+                                   const __grid_constant__ B2sState key) {
+    const uint32_t j = threadIdx.x;
+    uint32_t levels = 0;
+    while (((size_t)1 << (levels + 1)) < size) levels++;  // log2(size) - 1 stored sibling levels
+    if (j == 0) {
+        const Digest leaf = ld_digest(values, index ^ 1);
+        st_digest(out, 0, hash_leaf32(key, leaf.w));
+    }
+    if (j < levels) {
+        const size_t heap = ((size + index) >> (1 + j)) ^ 1;
+        st_digest(out, 1 + j, ld_digest(nodes, heap));
+    }
+}
+
+int merkle_path_gather(Ctx& c, const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
+                       cudaStream_t st) {
+    {
+        ProfScope ps(c, st, "merkle_path");
+        merkle_path_kernel<<<1, 64, 0, st>>>(nodes, values, size, index, out, c.key);
+    }
+    HODOR_CUDA_TRY(cudaGetLastError());
+    return HODOR_OK;
+}
+
+}  // namespace hodor

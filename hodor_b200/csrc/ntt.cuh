@@ -1,0 +1,360 @@
+// NTT / coset-LDE kernels for sm_100a.
+//
+// Replaces (same result bits, different algorithm) the reference's
+//   serial_fft / parallel_fft / best_fft            src/fft/fft.rs:5-125
+//   distribute_powers                               src/fft/mod.rs:110-123
+//   (coset_)lde_using_multiple_cosets               src/polynomials/mod.rs:418-482, 544-609
+//
+// Algorithm: recursive Cooley-Tukey over index digits.  The n = 2^log_n point transform is split
+// into P passes over HBM; pass p transforms one digit of B_p bits (B_p in 6..9) of the index with a
+// block-local 2^B_p-point decimation-in-frequency NTT, multiplies by the inter-pass twiddle
+// omega_N^(k*r) and writes back in place; the last pass writes to the digit-reversed (= natural
+// order) location.  Inside a block the 2^B-point NTT is done as two or three radix-8/4 groups held
+// in registers, exchanged through shared memory.  A block always works on 8 adjacent "columns"
+// (or 8 cosets / 8 adjacent output indices in the last pass) so that every global access is a
+// 256-byte contiguous run and every shared-memory quarter-warp access is a conflict-free 128 B.
+// An L-coset LDE is the same transform with one more, trivial, leading digit (the coset index):
+// its "twiddle" is the coset scaling shift_i^j, fused into the loads of pass 1, and the last pass
+// interleaves the cosets (out[i + L*k]) exactly as the reference's final gather does.
+#pragma once
+#include <cuda_runtime.h>
+#include "field.cuh"
+
+namespace hodor {
+
+struct TwoLevel {  // base^e = hi[e >> lo_bits] * lo[e & ((1 << lo_bits) - 1)]
+    const uint4* lo;
+    const uint4* hi;
+    uint32_t lo_bits;
+};
+
+enum : uint32_t {
+    PASS_OUT_CONST = 1u,  // last pass: multiply outputs by out_const (ifft: n^-1)
+    PASS_OUT_POW = 2u,    // last pass: multiply output k by out_pow^k (icoset_fft: g^-k, n^-1 folded into lo)
+};
+
+struct NttPass {
+    const uint4* in;
+    uint4* out;
+    uint32_t log_n;    // transform length per coset
+    uint32_t s;        // index bits below this pass's digit (0 for the last pass)
+    uint32_t log_l;    // log2(number of cosets)
+    uint32_t b1;       // width of the first digit (last pass: output index composition)
+    uint32_t mid0;     // width of the 2nd digit when it is a middle digit of the last pass, else 0
+    uint32_t mid1;     // width of the 3rd digit when it is a middle digit of the last pass, else 0
+    uint32_t flags;
+    uint32_t tw_shift;  // inter-pass twiddle exponent = (k * r) << tw_shift
+    uint32_t zero;      // always 0; opaque to ptxas (keeps the modulus in vector registers)
+    uint32_t coset_stride_lo, coset_stride_hi;  // elements between per-coset tables
+    TwoLevel tw;        // powers of omega
+    const uint4* tw_b;  // omega_B^x, x in [0, 2^B)
+    TwoLevel coset;     // pass 1 of a scaled transform: shift_i^j tables, coset i at +i*coset_stride
+    TwoLevel out_pow;   // PASS_OUT_POW
+    Fe out_const;       // PASS_OUT_CONST
+    Fe wr[7];           // omega_16^k, k = 1..7  (omega_8 = wr[1], omega_4 = wr[3])
+};
+
+DEV Fe ld_fe(const uint4* base, size_t idx) {
+    const uint4 a = base[2 * idx], b = base[2 * idx + 1];
+    Fe r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+DEV void st_fe(uint4* base, size_t idx, const Fe& r) {
+    base[2 * idx] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    base[2 * idx + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// shared-memory tile: two planes of uint4 so that a quarter warp touching 8 adjacent columns
+// reads 128 contiguous bytes
+DEV Fe lds_fe(const uint4* sm, uint32_t plane, uint32_t slot) {
+    const uint4 a = sm[slot], b = sm[plane + slot];
+    Fe r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+DEV void sts_fe(uint4* sm, uint32_t plane, uint32_t slot, const Fe& r) {
+    sm[slot] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    sm[plane + slot] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// copy a kernel-parameter (constant bank) element into vector registers
+DEV Fe ld_param(const Fe& c, uint32_t opaque_zero) {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = c.v[i] | opaque_zero;
+    return r;
+}
+
+template <class F>
+DEV Fe two_level_pow(const Field<F>& fld, const TwoLevel& t, size_t lo_off, size_t hi_off, uint64_t e) {
+    const Fe l = ld_fe(t.lo, lo_off + (e & ((1ull << t.lo_bits) - 1)));
+    const Fe h = ld_fe(t.hi, hi_off + (e >> t.lo_bits));
+    return fld.mul(l, h);
+}
+
+constexpr HD int bitrev_c(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// In-register radix-2^LOGR decimation-in-frequency NTT.  On return x[j] = X[bitrev(j)].
+template <class F, int LOGR>
+DEV void dif_inreg(const Field<F>& fld, Fe (&x)[1 << LOGR], const NttPass& p, uint32_t opaque_zero) {
+    constexpr int R = 1 << LOGR;
+#pragma unroll
+    for (int t = 0; t < LOGR; t++) {
+        const int half = R >> (t + 1);
+#pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * half) {
+#pragma unroll
+            for (int i = 0; i < half; i++) {
+                const Fe u = x[blk + i], v = x[blk + i + half];
+                x[blk + i] = fld.add(u, v);
+                const Fe d = fld.sub(u, v);
+                const int e = (i << t) * (16 / R);  // omega_R^(i<<t) as a power of omega_16
+                if (e == 0) {
+                    x[blk + i + half] = d;
+                } else {
+                    x[blk + i + half] = fld.mul(d, ld_param(p.wr[e - 1], opaque_zero));
+                }
+            }
+        }
+    }
+}
+
+template <int B>
+struct Groups {
+    static constexpr int R1 = 3;
+    static constexpr int REM = B - 3;
+    static constexpr int R2 = REM <= 3 ? REM : (REM + 1) / 2;
+    static constexpr int R3 = REM - R2;
+    static constexpr int NGROUPS = R3 > 0 ? 3 : 2;
+};
+
+// One group of the block-local NTT: every thread owns 8 elements = 8 >> LOGR butterflies of radix
+// 2^LOGR whose members are 2^SL positions apart.  SRC/DST: 0 = shared tile, 1 = global.
+template <class F, int B, int LOGR, int SL, int TWSH, bool FROM_GLOBAL, bool TO_GLOBAL, class LoadG, class StoreG>
+DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t tid, uint32_t oz, LoadG&& load_global,
+                   StoreG&& store_global) {
+    constexpr int R = 1 << LOGR;
+    constexpr int NB = 8 / R;
+    constexpr uint32_t T = 1u << B;
+    constexpr uint32_t PLANE = 8u << B;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const uint32_t q = tid + j * T;
+        const uint32_t c = q & 7u, rest = q >> 3;
+        const uint32_t lo = rest & ((1u << SL) - 1u), hi = rest >> SL;
+        const uint32_t base = (hi << (SL + LOGR)) | lo;
+        Fe x[R];
+#pragma unroll
+        for (int d = 0; d < R; d++) {
+            const uint32_t pos = base + ((uint32_t)d << SL);
+            if constexpr (FROM_GLOBAL) x[d] = load_global(pos, c);
+            else x[d] = lds_fe(sm, PLANE, pos * 8 + c);
+        }
+        dif_inreg<F, LOGR>(fld, x, p, oz);
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            Fe v = x[bitrev_c(k, LOGR)];
+            const uint32_t pos = base + ((uint32_t)k << SL);
+            if constexpr (SL > 0) {
+                if (k > 0) v = fld.mul(v, ld_fe(p.tw_b, (size_t)((k * lo) << TWSH)));
+            }
+            if constexpr (TO_GLOBAL) store_global(pos, c, v);
+            else sts_fe(sm, PLANE, pos * 8 + c, v);
+        }
+    }
+}
+
+// position (digits kappa1 | kappa2 | kappa3, MSB first) -> local output index
+template <int B>
+DEV uint32_t local_out_index(uint32_t pos) {
+    using G = Groups<B>;
+    constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3;
+    const uint32_t k1 = pos >> (R2 + R3);
+    const uint32_t k2 = (pos >> R3) & ((1u << R2) - 1u);
+    const uint32_t k3 = pos & ((1u << R3) - 1u);
+    return k1 | (k2 << R1) | (k3 << (R1 + R2));
+}
+
+template <class F, int B, bool SCALE_IN, bool LAST>
+__global__ void __launch_bounds__(1 << B) ntt_pass_kernel(const __grid_constant__ NttPass p) {
+    using G = Groups<B>;
+    extern __shared__ uint4 sm[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t oz = tid & p.zero;
+    const Field<F> fld(oz);
+    const uint32_t ln = p.log_n;
+    const size_t n = (size_t)1 << ln;
+
+    // ---- tile geometry -------------------------------------------------------------------
+    size_t in_base, out_base;     // element offsets that do not depend on (pos, c)
+    uint32_t coset_hi = 0;        // LAST: high part of the coset index; else the coset index
+    uint32_t k1_hi = 0, mid = 0;  // LAST only
+    uint32_t col0 = 0;            // !LAST: first column of the tile
+    const uint32_t li = p.log_l < 3 ? p.log_l : 3;  // coset bits inside c (LAST)
+    if constexpr (!LAST) {
+        const uint32_t s = p.s;
+        const uint32_t col_groups = 1u << (s - 3);
+        const uint32_t u = blockIdx.x >> (s - 3), cg = blockIdx.x & (col_groups - 1u);
+        coset_hi = blockIdx.y;
+        col0 = cg * 8;
+        in_base = ((size_t)u << (s + B)) + col0;
+        out_base = (size_t)coset_hi * n + in_base;
+        if constexpr (!SCALE_IN) in_base = out_base;  // per-coset data already in the work buffer
+    } else {
+        const uint32_t m = ln - B - p.b1;
+        const uint32_t kb = 3 - li;
+        uint32_t t = blockIdx.x;
+        mid = t & ((1u << m) - 1u);
+        t >>= m;
+        k1_hi = t & ((1u << (p.b1 - kb)) - 1u);
+        coset_hi = t >> (p.b1 - kb);
+        in_base = 0;
+        out_base = 0;
+    }
+
+    auto load_global = [&](uint32_t pos, uint32_t c) -> Fe {
+        if constexpr (!LAST) {
+            const size_t idx = in_base + ((size_t)pos << p.s) + c;
+            Fe v = ld_fe(p.in, idx);
+            if constexpr (SCALE_IN) {
+                // j = idx (u == 0 in pass 1): a[j] * shift_i^j
+                const Fe w = two_level_pow(fld, p.coset, (size_t)coset_hi * p.coset_stride_lo,
+                                           (size_t)coset_hi * p.coset_stride_hi, idx);
+                v = fld.mul(v, w);
+            }
+            return v;
+        } else {
+            const uint32_t m = ln - B - p.b1;
+            const uint32_t i = (coset_hi << li) | (c & ((1u << li) - 1u));
+            const uint32_t k1 = (k1_hi << (3 - li)) | (c >> li);
+            const size_t row = ((size_t)k1 << m) | mid;
+            return ld_fe(p.in, (size_t)i * n + (row << B) + pos);
+        }
+    };
+    auto store_global = [&](uint32_t pos, uint32_t c, Fe v) {
+        const uint32_t kloc = local_out_index<B>(pos);
+        if constexpr (!LAST) {
+            const uint64_t e = ((uint64_t)kloc * (col0 + c)) << p.tw_shift;
+            v = fld.mul(v, two_level_pow(fld, p.tw, 0, 0, e));
+            st_fe(p.out, out_base + ((size_t)kloc << p.s) + c, v);
+        } else {
+            const uint32_t i = (coset_hi << li) | (c & ((1u << li) - 1u));
+            const uint32_t k1 = (k1_hi << (3 - li)) | (c >> li);
+            // middle digits: mid = (k2 | k3) MSB first -> k2 + 2^mid0 * k3
+            uint32_t midrev = mid;
+            if (p.mid1) midrev = (mid >> p.mid1) | ((mid & ((1u << p.mid1) - 1u)) << p.mid0);
+            const size_t k = (size_t)k1 | ((size_t)midrev << p.b1) | ((size_t)kloc << (ln - B));
+            if (p.flags & PASS_OUT_CONST) v = fld.mul(v, ld_param(p.out_const, oz));
+            if (p.flags & PASS_OUT_POW) v = fld.mul(v, two_level_pow(fld, p.out_pow, 0, 0, k));
+            st_fe(p.out, (size_t)i + (k << p.log_l), v);
+        }
+    };
+
+    constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3;
+    ntt_group<F, B, R1, B - R1, 0, true, false>(fld, p, sm, tid, oz, load_global, store_global);
+    __syncthreads();
+    if constexpr (G::NGROUPS == 2) {
+        ntt_group<F, B, R2, 0, R1, false, true>(fld, p, sm, tid, oz, load_global, store_global);
+    } else {
+        ntt_group<F, B, R2, R3, R1, false, false>(fld, p, sm, tid, oz, load_global, store_global);
+        __syncthreads();
+        ntt_group<F, B, R3, 0, R1 + R2, false, true>(fld, p, sm, tid, oz, load_global, store_global);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small transforms (log_n <= 11): one block per coset, radix-2 DIF in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct SmallNtt {
+    const uint4* in;
+    uint4* out;
+    uint32_t log_n, log_l, flags, zero;
+    uint32_t coset_stride_lo, coset_stride_hi;
+    const uint4* tw;  // omega^e, e in [0, n/2]
+    TwoLevel coset;   // null lo => no input scaling
+    TwoLevel out_pow;
+    Fe out_const;
+};
+
+template <class F>
+__global__ void __launch_bounds__(1024) ntt_small_kernel(const __grid_constant__ SmallNtt p) {
+    extern __shared__ uint4 sm[];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t oz = tid & p.zero;
+    const Field<F> fld(oz);
+    const uint32_t ln = p.log_n, n = 1u << ln, coset = blockIdx.x;
+    for (uint32_t j = tid; j < n; j += nt) {
+        Fe v = ld_fe(p.in, j);
+        if (p.coset.lo != nullptr)
+            v = fld.mul(v, two_level_pow(fld, p.coset, (size_t)coset * p.coset_stride_lo,
+                                         (size_t)coset * p.coset_stride_hi, j));
+        st_fe(sm, j, v);
+    }
+    __syncthreads();
+    for (uint32_t st = 0; st < ln; st++) {
+        const uint32_t half = n >> (st + 1);
+        for (uint32_t q = tid; q < n / 2; q += nt) {
+            const uint32_t i = q & (half - 1u), blk = (q / half) * 2 * half;
+            const Fe u = ld_fe(sm, blk + i), v = ld_fe(sm, blk + i + half);
+            st_fe(sm, blk + i, fld.add(u, v));
+            Fe d = fld.sub(u, v);
+            if (i != 0) d = fld.mul(d, ld_fe(p.tw, (size_t)i << st));
+            st_fe(sm, blk + i + half, d);
+        }
+        __syncthreads();
+    }
+    for (uint32_t j = tid; j < n; j += nt) {
+        const uint32_t k = ln ? (__brev(j) >> (32 - ln)) : 0u;
+        Fe v = ld_fe(sm, j);
+        if (p.flags & PASS_OUT_CONST) v = fld.mul(v, ld_param(p.out_const, oz));
+        if (p.flags & PASS_OUT_POW) v = fld.mul(v, two_level_pow(fld, p.out_pow, 0, 0, k));
+        st_fe(p.out, (size_t)coset + ((size_t)k << p.log_l), v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tables and elementwise helpers
+// ------------------------------------------------------------------------------------------------
+// out[b * count + i] = bases[b]^i * (scale ? scale[0] : 1)
+template <class F>
+__global__ void pow_table_kernel(uint4* out, const Fe* bases, const Fe* scale, uint32_t count, uint32_t zero) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Field<F> fld(threadIdx.x & zero);
+    Fe r = fld.pow(bases[blockIdx.y], i);
+    if (scale != nullptr) r = fld.mul(r, scale[0]);
+    st_fe(out, (size_t)blockIdx.y * count + i, r);
+}
+
+// a[j] <- a[j] * c * g^j     (distribute_powers, src/fft/mod.rs:110-123; c folded into pw.lo)
+template <class F>
+__global__ void scale_pow_kernel(uint4* a, size_t n, TwoLevel pw, uint32_t zero) {
+    const Field<F> fld(threadIdx.x & zero);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        const Fe v = ld_fe(a, j);
+        st_fe(a, j, fld.mul(v, two_level_pow(fld, pw, 0, 0, j)));
+    }
+}
+
+enum : int { EW_MUL = 0, EW_ADD = 1, EW_SUB = 2, EW_SCALE = 3 };
+// elementwise Polynomial ops (src/polynomials/mod.rs:59-83, 744-771, 817-887): out = a (op) b
+template <class F>
+__global__ void elementwise_kernel(int op, const uint4* a, const uint4* b, uint4* out, size_t n, uint32_t zero) {
+    const Field<F> fld(threadIdx.x & zero);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        const Fe x = ld_fe(a, j);
+        const Fe y = ld_fe(b, op == EW_SCALE ? 0 : j);
+        Fe r;
+        if (op == EW_MUL || op == EW_SCALE) r = fld.mul(x, y);
+        else if (op == EW_ADD) r = fld.add(x, y);
+        else r = fld.sub(x, y);
+        st_fe(out, j, r);
+    }
+}
+
+}  // namespace hodor

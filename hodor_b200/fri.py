@@ -1,0 +1,143 @@
+"""Mirror of the reference's FRI prover surface: trait FriIop and the proof structs in
+src/fri/mod.rs:26-154, NaiveFriIop::proof_from_lde_by_values in src/fri/fri_on_values.rs:11-159 and
+FRIProofPrototype::produce_proof in src/fri/query_producer.rs:10-53.
+
+The whole commit chain (l0 tree, then per layer: fold, tree, root -> challenge; final iNTT) is
+enqueued on one CUDA stream by hodor_cuda_fri_commit and stays in HBM behind a handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from ._ffi import HodorError, check, ensure_init, last_error, lib, u8p
+from .domains import Domain
+from .field import _p
+from .iop import DeviceIOP, TrivialBlake2sIopQuery, TrivialCombiner
+from .polynomials import VALUES, Polynomial, Worker
+
+
+class FRIProof:
+    """src/fri/mod.rs:140-154"""
+
+    def __init__(self, queries, roots, final_coefficients, initial_degree_plus_one, output_coeffs_at_degree_plus_one,
+                 lde_factor):
+        self.queries = queries
+        self.roots = roots
+        self.final_coefficients = final_coefficients
+        self.initial_degree_plus_one = initial_degree_plus_one
+        self.output_coeffs_at_degree_plus_one = output_coeffs_at_degree_plus_one
+        self.lde_factor = lde_factor
+
+    def get_final_coefficients(self) -> np.ndarray:
+        return self.final_coefficients
+
+
+class FRIProofPrototype:
+    """src/fri/mod.rs:107-138, backed by a device handle."""
+
+    def __init__(self, field_id: int, handle: int, n: int, lde_factor: int, out_coeffs: int):
+        self.field_id = field_id
+        self._handle = handle
+        self._n = n
+        self.lde_factor = lde_factor
+        self.output_coeffs_at_degree_plus_one = out_coeffs
+        self.initial_degree_plus_one = n // lde_factor
+        steps = check(lib.hodor_cuda_fri_num_steps(handle))
+        self.num_steps = steps
+        roots = np.zeros((steps + 1, 32), np.uint8)
+        self.challenges = np.zeros((steps, 4), np.uint64)
+        self.final_coefficients = np.zeros((out_coeffs, 4), np.uint64)
+        check(lib.hodor_cuda_fri_summary(handle, roots.ctypes.data_as(u8p), _p(self.challenges), _p(self.final_coefficients)))
+        self._roots = [r.tobytes() for r in roots]
+        self.final_root = self._roots[-1]
+        self.l0_commitment = DeviceIOP(field_id, self, 0, n, self._roots[0])
+        self.intermediate_commitments = [DeviceIOP(field_id, self, i + 1, n >> (i + 1), self._roots[i + 1])
+                                         for i in range(steps)]
+        self._values: List[Optional[Polynomial]] = [None] * steps
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            lib.hodor_cuda_fri_free(h)
+
+    # FriProofPrototype trait (:26-30, :119-138)
+    def get_roots(self) -> List[bytes]:
+        return list(self._roots)
+
+    def get_final_root(self) -> bytes:
+        return self.final_root
+
+    def get_final_coefficients(self) -> np.ndarray:
+        return self.final_coefficients.copy()
+
+    @property
+    def intermediate_values(self) -> List[Polynomial]:
+        for i in range(self.num_steps):
+            if self._values[i] is None:
+                self._values[i] = Polynomial(self.field_id, self._fetch_layer(i + 1, want_values=True)[1], VALUES)
+        return self._values  # type: ignore[return-value]
+
+    def _fetch_layer(self, layer: int, want_nodes: bool = False, want_values: bool = False):
+        size = int(lib.hodor_cuda_fri_layer_size(self._handle, layer))
+        nodes = np.zeros((size, 32), np.uint8) if want_nodes else None
+        values = np.zeros((size, 4), np.uint64) if want_values else None
+        check(lib.hodor_cuda_fri_layer(self._handle, layer, nodes.ctypes.data_as(u8p) if want_nodes else None,
+                                       _p(values) if want_values else None))
+        return nodes, values
+
+    def _query(self, layer: int, natural_index: int) -> TrivialBlake2sIopQuery:
+        size = int(lib.hodor_cuda_fri_layer_size(self._handle, layer))
+        value = np.zeros(4, np.uint64)
+        path = np.zeros((size.bit_length() - 1, 32), np.uint8)
+        n = check(lib.hodor_cuda_fri_query(self._handle, layer, C.c_uint64(natural_index), _p(value), path.ctypes.data_as(u8p)))
+        assert n == path.shape[0]
+        return TrivialBlake2sIopQuery(natural_index, value, [p.tobytes() for p in path])
+
+    def produce_proof(self, iop_values: Optional[Polynomial], natural_first_element_index: int) -> FRIProof:
+        """src/fri/query_producer.rs:10-53 (the leaf values are read from HBM, so `iop_values` is unused)."""
+        domain_size = self.initial_degree_plus_one * self.lde_factor
+        domain_idx = natural_first_element_index
+        queries, roots = [], []
+        for layer in range(self.num_steps + 1):
+            coset = TrivialCombiner.get_coset_for_natural_index(domain_idx, domain_size)
+            for idx in coset:
+                queries.append(self._query(layer, idx))
+            roots.append(self._roots[layer])
+            domain_idx, domain_size = Domain.index_and_size_for_next_domain(domain_idx, domain_size)
+        return FRIProof(queries, roots, self.final_coefficients.copy(), self.initial_degree_plus_one,
+                        self.output_coeffs_at_degree_plus_one, self.lde_factor)
+
+
+class NaiveFriIop:
+    """src/fri/mod.rs:63-105"""
+
+    DEGREE = 2
+
+    @staticmethod
+    def proof_from_lde(lde_values: Polynomial, lde_factor: int, output_coeffs_at_degree_plus_one: int,
+                       worker: Optional[Worker] = None) -> FRIProofPrototype:
+        return NaiveFriIop.proof_from_lde_by_values(lde_values, lde_factor, output_coeffs_at_degree_plus_one, worker)
+
+    @staticmethod
+    def proof_from_lde_by_values(lde_values: Polynomial, lde_factor: int, output_coeffs_at_degree_plus_one: int,
+                                 worker: Optional[Worker] = None) -> FRIProofPrototype:
+        if lde_values.form != VALUES:
+            raise TypeError("proof_from_lde needs Polynomial<F, Values>")
+        ensure_init()
+        n = lde_values.size()
+        h = lib.hodor_cuda_fri_commit(lde_values.as_ref().ctypes.data, C.c_uint64(n), lde_factor,
+                                      output_coeffs_at_degree_plus_one, 0, lde_values.field_id)
+        if not h:
+            msg = last_error()
+            if "2-adicity" in msg:
+                check(-2)
+            raise HodorError(-1 if "fri_commit:" in msg else -3, msg)
+        return FRIProofPrototype(lde_values.field_id, h, n, lde_factor, output_coeffs_at_degree_plus_one)
+
+    @staticmethod
+    def prototype_into_proof(prototype: FRIProofPrototype, iop_values: Optional[Polynomial],
+                             natural_first_element_index: int) -> FRIProof:
+        return prototype.produce_proof(iop_values, natural_first_element_index)

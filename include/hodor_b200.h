@@ -1,0 +1,170 @@
+/*
+ * hodor_b200 -- C ABI of the B200 (sm_100a) STARK-prover hot path.
+ *
+ * Drop-in boundary for matter-labs/hodor (@76fc894).  The reference has no FFI; these entry points
+ * are what a `feature = "cuda"` arm of its `cfg_if!` dispatch (src/fft/mod.rs:28-58) and new
+ * `IOP` / `FriIop` type arguments of `Prover` (src/prover/mod.rs:29,44) would bind.  Each function
+ * cites the reference item it replaces.  INTEGRATION.md shows the Rust side.
+ *
+ * Conventions
+ *   - A field element is 4 little-endian u64 limbs in Montgomery form (R = 2^256), canonical (< p):
+ *     the in-memory layout of ff_ce's derive(PrimeField) `Fr(FrRepr([u64; 4]))`, so `&[F]` can be
+ *     passed as `*const u64` with no conversion.  Vectors are contiguous, 32 bytes per element.
+ *   - Digests are 32 bytes.  A tree's `nodes` is n digests in heap order (nodes[0] zero,
+ *     nodes[1] root, level with w nodes at [w, 2w)), exactly `Blake2sIopTree.nodes`.
+ *   - Sizes are element counts.  All transforms are natural order in, natural order out.
+ *   - Return value: 0 (or a non-negative count) on success, a negative HODOR_ERR_* otherwise;
+ *     hodor_cuda_last_error() gives the message.  The library never aborts the process and never
+ *     computes on the CPU: without a usable GPU every compute entry point fails with
+ *     HODOR_ERR_CUDA.
+ *   - One process drives one GPU (hodor_cuda_init(device)).  Entry points may be called from any
+ *     host thread; calls are serialised on the context.  `_dev` variants take device pointers and a
+ *     cudaStream_t (as void*), enqueue work and return without synchronising.
+ */
+#ifndef HODOR_B200_H
+#define HODOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field_id.  HODOR_FIELD_BLS12_381_FR is the field that src/bn256.rs:4-7 declares under the name
+ * bn256::Fr (its modulus is the BLS12-381 scalar field); HODOR_FIELD_BN254_FR is the curve usually
+ * meant by "bn256"; HODOR_FIELD_STARK252 is experiments::Fr (src/experiments/mod.rs:18-21). */
+#define HODOR_FIELD_BLS12_381_FR 0
+#define HODOR_FIELD_BN254_FR 1
+#define HODOR_FIELD_STARK252 2
+
+#define HODOR_OK 0
+#define HODOR_ERR_INVALID_ARG (-1)  /* reference: assert!/expect panic */
+#define HODOR_ERR_DOMAIN (-2)       /* reference: Domain::new_for_size -> Err(SynthesisError::Error), src/domains/mod.rs:29-32 */
+#define HODOR_ERR_CUDA (-3)         /* no device, launch or runtime failure */
+#define HODOR_ERR_OOM (-4)
+#define HODOR_ERR_NOT_A_ROOT (-5)   /* omega is not a primitive 2^log_n-th root of unity */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int hodor_cuda_device_count(void);
+int hodor_cuda_init(int device);
+void hodor_cuda_shutdown(void);
+const char* hodor_cuda_last_error(void);
+/* bytes of device workspace + cached twiddle tables currently held */
+size_t hodor_cuda_workspace_bytes(void);
+
+/* ---- host-side scalar helpers (what ff_ce / Domain give the Rust caller) --------------------- */
+/* PrimeField consts: modulus (plain), one = R mod p, multiplicative_generator(), root_of_unity()
+ * (all Montgomery), S, NUM_BITS, CAPACITY. */
+int hodor_field_constants(int field_id, uint64_t modulus[4], uint64_t one[4], uint64_t generator[4],
+                          uint64_t root_of_unity[4], uint32_t* s, uint32_t* num_bits, uint32_t* capacity);
+/* Domain::new_for_size(2^log_n).generator  (src/domains/mod.rs:21-44) */
+int hodor_domain_generator(int field_id, uint32_t log_n, uint64_t out[4]);
+int hodor_field_mul(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+int hodor_field_add(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+int hodor_field_sub(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+int hodor_field_pow(int field_id, const uint64_t a[4], uint64_t e, uint64_t out[4]);
+int hodor_field_inverse(int field_id, const uint64_t a[4], uint64_t out[4]); /* HODOR_ERR_INVALID_ARG on zero */
+int hodor_field_from_repr(int field_id, const uint64_t plain[4], uint64_t out[4]); /* PrimeField::from_repr */
+int hodor_field_into_repr(int field_id, const uint64_t mont[4], uint64_t out[4]);  /* PrimeField::into_repr */
+/* Blake2sLeafEncoder::interpret_hash / IopTree::encode_root_into_challenge
+ * (src/iop/blake2s_trivial_iop.rs:48-60, :226-228) */
+int hodor_root_to_challenge(const uint8_t root[32], uint64_t out[4], int field_id);
+
+/* ---- memory helpers ---------------------------------------------------------------------- */
+void* hodor_cuda_malloc(size_t bytes);
+void hodor_cuda_free(void* dptr);
+void* hodor_cuda_host_alloc(size_t bytes); /* pinned */
+void hodor_cuda_host_free(void* hptr);
+int hodor_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream);
+int hodor_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);
+int hodor_cuda_stream_synchronize(void* stream);
+
+/* ---- transforms, host memory ------------------------------------------------------------- */
+/* best_fft / serial_fft (src/fft/fft.rs:5-66, dispatch src/fft/mod.rs:50-56):
+ * a[k] <- sum_j a[j] * omega^(j*k), in place.  omega must be a primitive 2^log_n-th root. */
+int hodor_cuda_ntt(uint64_t* a, uint32_t log_n, const uint64_t omega[4], int field_id);
+/* Polynomial::fft / coset_fft (src/polynomials/mod.rs:611-631): omega = domain generator;
+ * coset != 0 first scales a[j] by multiplicative_generator^j. */
+int hodor_cuda_fft(uint64_t* a, uint32_t log_n, int coset, int field_id);
+/* Polynomial::ifft / icoset_fft (src/polynomials/mod.rs:773-807): NTT with omega^-1, times n^-1;
+ * coset != 0 then scales a[j] by generator^-j. */
+int hodor_cuda_ifft(uint64_t* a, uint32_t log_n, int coset, int field_id);
+/* distribute_powers (src/fft/mod.rs:110-123): a[j] <- a[j] * g^j */
+int hodor_cuda_distribute_powers(uint64_t* a, uint64_t n, const uint64_t g[4], int field_id);
+/* Polynomial::lde / coset_lde == (coset_)lde_using_multiple_cosets
+ * (src/polynomials/mod.rs:343-352, 418-482, 544-609): out has n << log_factor elements,
+ * out[i + L*k] = P(shift * w_{nL}^(i + L*k)), shift = 1 or multiplicative_generator. */
+int hodor_cuda_lde(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint64_t* out, int field_id);
+/* elementwise Polynomial ops (src/polynomials/mod.rs:640-683, 817-887): op 0 mul, 1 add, 2 sub,
+ * 3 scale (b is one element).  out may alias a. */
+int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id);
+
+/* ---- Merkle oracle, host memory ----------------------------------------------------------- */
+/* Blake2sIopTree::create (src/iop/blake2s_trivial_iop.rs:131-219).  n a power of two >= 2;
+ * nodes receives n * 32 bytes. */
+int hodor_cuda_merkle_build(const uint64_t* leaves, uint64_t n, uint8_t* nodes, int field_id);
+
+/* ---- FRI commit chain ---------------------------------------------------------------------- */
+/* NaiveFriIop::proof_from_lde_by_values (src/fri/fri_on_values.rs:11-159), result kept on the
+ * device behind a handle (the FRIProofPrototype, src/fri/mod.rs:107-117).  lde may be a host or a
+ * device pointer (lde_on_device).  Returns the handle or NULL. */
+typedef struct hodor_fri_proto hodor_fri_proto;
+hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
+                                       int lde_on_device, int field_id);
+void hodor_cuda_fri_free(hodor_fri_proto* p);
+int hodor_cuda_fri_num_steps(const hodor_fri_proto* p);
+/* roots: (num_steps + 1) * 32 bytes: l0 root, then every intermediate root (FriProofPrototype::
+ * get_roots; the last one is also final_root).  challenges: num_steps * 4 u64.
+ * final_coeffs: out_coeffs * 4 u64. */
+int hodor_cuda_fri_summary(const hodor_fri_proto* p, uint8_t* roots, uint64_t* challenges, uint64_t* final_coeffs);
+/* layer 0 = the l0 commitment over the caller's lde values; layer i >= 1 = intermediate i-1.
+ * Copies the layer's nodes (size * 32 B) and, for i >= 1, values (size * 4 u64) to the host.
+ * Either pointer may be NULL. */
+int hodor_cuda_fri_layer(const hodor_fri_proto* p, uint32_t layer, uint8_t* nodes, uint64_t* values);
+uint64_t hodor_cuda_fri_layer_size(const hodor_fri_proto* p, uint32_t layer);
+/* IOP::query (src/iop/blake2s_trivial_iop.rs:251-279, 324-338) against layer `layer`:
+ * value (4 u64) and path (log2(size) * 32 B, leaf-pair hash first).  Returns the path length. */
+int hodor_cuda_fri_query(const hodor_fri_proto* p, uint32_t layer, uint64_t natural_index, uint64_t value[4],
+                         uint8_t* path);
+/* Same as the reference signature: everything copied out to caller-allocated host buffers.
+ * layer_nodes[i] / layer_values[i] hold (n >> (i+1)) entries.  Returns num_steps. */
+int hodor_cuda_fri_commit_host(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
+                               uint8_t* l0_nodes, uint8_t** layer_nodes, uint64_t** layer_values,
+                               uint64_t* challenges, uint8_t* final_root, uint64_t* final_coeffs, int field_id);
+
+/* ---- device-resident variants (no host copies, stream ordered) ------------------------------ */
+int hodor_cuda_ntt_dev(const void* d_in, void* d_out, uint32_t log_n, const uint64_t omega[4], int field_id,
+                       void* stream);
+int hodor_cuda_fft_dev(const void* d_in, void* d_out, uint32_t log_n, int coset, int field_id, void* stream);
+int hodor_cuda_ifft_dev(const void* d_in, void* d_out, uint32_t log_n, int coset, int field_id, void* stream);
+int hodor_cuda_lde_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, void* d_out,
+                       int field_id, void* stream);
+/* d_root (32 B) and d_challenge (32 B, Montgomery) may be NULL */
+int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes, void* d_root, void* d_challenge,
+                                int field_id, void* stream);
+/* one FRI layer: d_out[idx], idx < n/2, from d_in (n values); challenge read from d_challenge */
+int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
+                            const void* d_challenge, void* d_out, int field_id, void* stream);
+int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
+                               void* stream);
+/* Four-step building blocks for an NTT sharded over G = 2^log_g GPUs (multi-GPU):
+ * step A on rank r: n/G-point column NTTs of the rank's slice + twiddle by omega^(j2 * k1);
+ * after the all-to-all, step B: row NTTs.  See hodor_b200/sharded.py for the orchestration. */
+int hodor_cuda_ntt_shard_cols_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
+                                  const uint64_t omega[4], int field_id, void* stream);
+int hodor_cuda_ntt_shard_rows_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
+                                  const uint64_t omega[4], int field_id, void* stream);
+
+/* kernels launched by this library since init (bench.py's gpu_launches) */
+uint64_t hodor_cuda_launch_count(void);
+/* Optional per-kernel timing: between begin and end every launch is bracketed by CUDA events on
+ * its stream; end synchronises the device and writes a JSON array
+ * [{"name": ..., "count": ..., "total_ms": ...}] into json_out.  Returns the number of entries. */
+int hodor_cuda_profile_begin(void);
+int hodor_cuda_profile_end(char* json_out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HODOR_B200_H */

@@ -1,0 +1,31 @@
+// Host build of hodor_b200/csrc/field.cuh (carry chains emulated in C) so the even/odd Montgomery
+// multiplier can be checked on a machine without a GPU.  Test-only; never shipped.
+#include <cstddef>
+#include "../../hodor_b200/csrc/field.cuh"
+using namespace hodor;
+
+template <class F>
+static void run(int op, const Fe* a, const Fe* b, Fe* out, size_t n) {
+    const Field<F> f;
+    for (size_t i = 0; i < n; i++) {
+        switch (op) {
+            case 0: out[i] = f.mul(a[i], b[i]); break;
+            case 1: out[i] = f.add(a[i], b[i]); break;
+            case 2: out[i] = f.sub(a[i], b[i]); break;
+            case 3: out[i] = f.halve(a[i]); break;
+            case 4: out[i] = f.to_mont(a[i]); break;
+            case 5: out[i] = f.from_mont(a[i]); break;
+            case 6: out[i] = f.neg(a[i]); break;
+        }
+    }
+}
+extern "C" int host_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    const Fe *A = (const Fe*)a, *B = (const Fe*)b;
+    Fe* O = (Fe*)out;
+    switch (field) {
+        case 0: run<BlsFr>(op, A, B, O, n); return 0;
+        case 1: run<Bn254Fr>(op, A, B, O, n); return 0;
+        case 2: run<Stark252>(op, A, B, O, n); return 0;
+    }
+    return -1;
+}

@@ -1,0 +1,399 @@
+"""GPU parity: the CUDA path, called through the C ABI (host-pointer entry points via the Python
+mirror of the reference interface, and the device-pointer entry points), against the CPU oracle on
+the same seeded inputs -- bit-exact -- plus size-independent properties at BASELINE.json's sizes.
+The shapes follow the reference's own tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import FIELD_IDS, FIELDS
+
+pytestmark = pytest.mark.gpu
+
+
+def structured_vectors(O, fid, n):
+    c = O.field_constants(fid)
+    p = O.limbs_to_int(c["p"])
+    zero = np.zeros((n, 4), np.uint64)
+    one = np.tile(c["r"], (n, 1))
+    d0 = zero.copy(); d0[0] = c["r"]
+    d1 = zero.copy(); d1[min(1, n - 1)] = c["r"]
+    pm1 = np.tile(O.int_to_limbs(p - 1), (n, 1))
+    return {"zero": zero, "one": one, "delta0": d0, "delta1": d1, "p-1": pm1}
+
+
+# ----------------------------------------------------------------------------------------------
+# field arithmetic on the device
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_elementwise_field_ops(hodor, oracle, fid):
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+
+    n = 1 << 14
+    a, b = oracle.random_elements(fid, n, 1), oracle.random_elements(fid, n, 2)
+    c = oracle.field_constants(fid)
+    p = oracle.limbs_to_int(c["p"])
+    edge = oracle.ints_to_array([0, 1, p - 1, oracle.limbs_to_int(c["r"]), p - 2, 2, (p - 1) // 2, (p + 1) // 2])
+    a[:8], b[:8] = edge, edge[::-1]
+    a[8:16], b[8:16] = edge, edge
+    a[16:24], b[16:24] = edge, np.tile(oracle.int_to_limbs(p - 1), (8, 1))
+    out = np.zeros_like(a)
+    for op, fn in ((0, oracle.mul), (1, oracle.add), (2, oracle.sub)):
+        _ffi.check(_ffi.lib.hodor_cuda_elementwise(op, _p(a), _p(b), _p(out), C.c_uint64(n), fid))
+        assert np.array_equal(out, fn(fid, a, b)), f"op {op}"
+    _ffi.check(_ffi.lib.hodor_cuda_elementwise(3, _p(a), _p(b[:1].copy()), _p(out), C.c_uint64(n), fid))
+    assert np.array_equal(out, oracle.mul(fid, a, np.tile(b[0], (n, 1))))
+
+
+# ----------------------------------------------------------------------------------------------
+# NTT
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+@pytest.mark.parametrize("log_n", list(range(0, 17)))
+def test_ntt_matches_oracle(hodor, oracle, fid, log_n):
+    """best_fft == serial_fft for every size class: single block (<= 2^11) and 2 passes."""
+    n = 1 << log_n
+    a = oracle.random_elements(fid, n, seed=100 + log_n)
+    omega = oracle.domain_generator(fid, log_n)
+    want = oracle.serial_fft(fid, a, omega, log_n)
+    got = hodor.Polynomial.from_coeffs(fid, a).fft().as_ref()
+    assert np.array_equal(got, want)
+    # arbitrary primitive root through the raw best_fft entry point: omega^-1
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+    winv = oracle.inverse(fid, omega)
+    buf = a.copy()
+    _ffi.check(_ffi.lib.hodor_cuda_ntt(_p(buf), log_n, _p(winv), fid))
+    assert np.array_equal(buf, oracle.serial_fft(fid, a, winv, log_n))
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_ntt_structured_inputs(hodor, oracle, fid):
+    for log_n in (3, 9, 12, 14):
+        omega = oracle.domain_generator(fid, log_n)
+        for name, v in structured_vectors(oracle, fid, 1 << log_n).items():
+            got = hodor.Polynomial.from_coeffs(fid, v).fft().as_ref()
+            assert np.array_equal(got, oracle.serial_fft(fid, v, omega, log_n)), (name, log_n)
+
+
+@pytest.mark.parametrize("log_n", [18, 19, 20, 21])
+def test_ntt_large_matches_oracle_multicore(hodor, oracle, log_n):
+    """2 and 3 HBM passes (all digit widths 6..9 are covered by 12..21) vs the reference's
+    parallel_fft restatement on all host cores."""
+    fid = 0
+    a = oracle.random_elements(fid, 1 << log_n, seed=log_n)
+    omega = oracle.domain_generator(fid, log_n)
+    want = oracle.best_fft(fid, a, omega, log_n)
+    assert np.array_equal(hodor.Polynomial.from_coeffs(fid, a).fft().as_ref(), want)
+
+
+def test_ntt_rejects_non_root(hodor, oracle):
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+    a = oracle.random_elements(0, 16, 1)
+    bad = oracle.domain_generator(0, 5)  # order 32, not 16
+    assert _ffi.lib.hodor_cuda_ntt(_p(a), 4, _p(bad), 0) == _ffi.ERR_NOT_A_ROOT
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_ifft_and_coset_roundtrips(hodor, oracle, fid):
+    """test_worker_size's round trip (src/fft/mod.rs:281) and Polynomial::{ifft, icoset_fft}."""
+    for log_n in (0, 1, 4, 10, 13, 16):
+        a = oracle.random_elements(fid, 1 << log_n, seed=7 + log_n)
+        vals = hodor.Polynomial.from_coeffs(fid, a).fft()
+        assert np.array_equal(vals.as_ref(), oracle.fft(fid, a, log_n))
+        assert np.array_equal(vals.clone().ifft().as_ref(), a)
+        cvals = hodor.Polynomial.from_coeffs(fid, a).coset_fft()
+        assert np.array_equal(cvals.as_ref(), oracle.fft(fid, a, log_n, coset=True))
+        assert np.array_equal(cvals.clone().icoset_fft().as_ref(), a)
+        assert np.array_equal(hodor.Polynomial.from_values(fid, a).ifft().as_ref(), oracle.ifft(fid, a, log_n))
+        assert np.array_equal(hodor.Polynomial.from_values(fid, a).icoset_fft().as_ref(),
+                              oracle.ifft(fid, a, log_n, coset=True))
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_distribute_powers(hodor, oracle, fid):
+    g = oracle.field_constants(fid)["generator"]
+    for n in (1, 2, 5, 1000, 1 << 15):
+        a = oracle.random_elements(fid, n, seed=n)
+        pad = 1 << max(0, (n - 1).bit_length())
+        p = hodor.Polynomial.from_coeffs(fid, a)
+        p.distribute_powers(None, g)
+        want = oracle.distribute_powers(fid, np.concatenate([a, np.zeros((pad - n, 4), np.uint64)]), g)
+        assert np.array_equal(p.as_ref(), want)
+
+
+# ----------------------------------------------------------------------------------------------
+# LDE
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+@pytest.mark.parametrize("coset", [False, True])
+def test_lde_matches_oracle(hodor, oracle, fid, coset):
+    """test_lde_correctness / test_coset_lde_correctness / test_various_ldes shapes
+    (src/polynomials/mod.rs:988-1128), incl. the reference's n = 4, L = 16."""
+    for log_n, L in [(2, 16), (0, 2), (1, 4), (3, 1), (5, 2), (8, 8), (11, 4), (12, 8), (13, 16), (14, 2), (15, 32)]:
+        a = oracle.random_elements(fid, 1 << log_n, seed=31 * log_n + L)
+        p = hodor.Polynomial.from_coeffs(fid, a)
+        got = (p.coset_lde(None, L) if coset else p.lde(None, L)).as_ref()
+        assert np.array_equal(got, oracle.lde(fid, a, log_n, L, coset)), (log_n, L)
+
+
+def test_lde_2p20_x8_bit_exact_and_horner(hodor, oracle, pymodel):
+    """configs[1] shape at a size the CPU oracle finishes in seconds: coset LDE, blowup 8."""
+    fid, log_n, L = 0, 18, 8
+    a = oracle.random_elements(fid, 1 << log_n, seed=2024)
+    got = hodor.Polynomial.from_coeffs(fid, a).coset_lde(None, L).as_ref()
+    assert np.array_equal(got, oracle.lde(fid, a, log_n, L, True))
+    # multi-coset LDE == coset NTT of the zero-padded vector (reference identity)
+    padded = np.zeros(((1 << log_n) * L, 4), np.uint64)
+    padded[: 1 << log_n] = a
+    assert np.array_equal(got, hodor.Polynomial.from_coeffs(fid, padded).coset_fft().as_ref())
+
+
+def test_lde_2p24_x8_properties(hodor, oracle, pymodel):
+    """BASELINE.json configs[1] at full size (2^24 -> 2^27, 4 GiB): size-independent checks.
+    (a) Horner spot checks of 24 outputs in Python big ints; (b) decimating the LDE by 8 gives the
+    plain coset NTT; (c) icoset_fft of that recovers the coefficients."""
+    F = pymodel.BLS12_381_FR
+    fid, log_n, L = 0, 24, 8
+    n = 1 << log_n
+    a = oracle.random_elements(fid, n, seed=99)
+    # keep the Horner check affordable: make the polynomial sparse-ish but full degree
+    a[1 << 12 : n - (1 << 12)] = 0
+    lde = hodor.Polynomial.from_coeffs(fid, a).coset_lde(None, L).as_ref()
+    assert lde.shape[0] == n * L
+    w = F.domain_generator(log_n + 3)
+    nz = [i for i in list(range(1 << 12)) + list(range(n - (1 << 12), n))]
+    coeffs = {i: F.from_mont(oracle.limbs_to_int(a[i])) for i in nz}
+    rng = np.random.default_rng(5)
+    for idx in [0, 1, n * L - 1] + [int(x) for x in rng.integers(0, n * L, 21)]:
+        x = F.generator * pow(w, idx, F.p) % F.p
+        lo = sum(c * pow(x, i, F.p) for i, c in coeffs.items() if i < (1 << 12)) % F.p
+        hi = sum(c * pow(x, i - (n - (1 << 12)), F.p) for i, c in coeffs.items() if i >= (1 << 12)) % F.p
+        want = (lo + hi * pow(x, n - (1 << 12), F.p)) % F.p
+        assert F.from_mont(oracle.limbs_to_int(lde[idx])) == want, idx
+    coset0 = np.ascontiguousarray(lde[::L])
+    back = hodor.Polynomial.from_values(fid, coset0).icoset_fft().as_ref()
+    assert np.array_equal(back, a)
+
+
+# ----------------------------------------------------------------------------------------------
+# Merkle oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 7, 11, 12, 13, 14, 15, 16, 17])
+def test_merkle_matches_oracle(hodor, oracle, fid, log_n):
+    leaves = oracle.random_elements(fid, 1 << log_n, seed=500 + log_n)
+    tree = hodor.Blake2sIopTree.create(fid, leaves)
+    want = oracle.merkle_create(fid, leaves)
+    assert np.array_equal(tree.nodes, want)
+    assert np.array_equal(tree.get_challenge_scalar_from_root(), oracle.interpret_hash(fid, want[1].tobytes()))
+
+
+def test_make_small_tree_and_iop(hodor, oracle):
+    """make_small_tree / make_small_iop (src/iop/blake2s_trivial_iop.rs:377-408) on the GPU tree."""
+    fid = 2
+    one = oracle.field_constants(fid)["r"]
+    tree = hodor.Blake2sIopTree.create(fid, np.tile(one, (16, 1)))
+    assert tree.get_root().hex() == "fdf489862b4402468d94f026c014e1ca0129f421a55ce5e1df838eab8eefbd22"
+    vals = oracle.to_mont(fid, oracle.ints_to_array([1 << i for i in range(64)]))
+    iop = hodor.TrivialBlake2sIOP.create(fid, vals)
+    root = iop.get_root()
+    for i in range(64):
+        q = iop.query(i, vals)
+        assert hodor.TrivialBlake2sIOP.verify_query(q, root), f"invalid query for leaf {i}"
+        assert q.path() == oracle.merkle_path(fid, iop.tree.nodes, vals, i)
+    with pytest.raises(AssertionError):
+        hodor.Blake2sIopTree.create(fid, vals[:48])  # assert!(num_leafs == next_power_of_two)
+
+
+def test_merkle_2p22_vs_oracle_and_2p24_paths(hodor, oracle):
+    fid = 0
+    leaves = oracle.random_elements(fid, 1 << 22, seed=4242)
+    tree = hodor.Blake2sIopTree.create(fid, leaves)
+    assert np.array_equal(tree.nodes, oracle.merkle_create(fid, leaves))
+    # full size of configs[2]'s first tree: every sampled authentication path must verify
+    leaves = oracle.random_elements(fid, 1 << 24, seed=4243)
+    iop = hodor.TrivialBlake2sIOP.create(fid, leaves)
+    root = iop.get_root()
+    assert not iop.tree.nodes[0].any()
+    rng = np.random.default_rng(8)
+    for i in [0, 1, (1 << 24) - 1] + [int(x) for x in rng.integers(0, 1 << 24, 13)]:
+        assert hodor.TrivialBlake2sIOP.verify_query(iop.query(i, leaves), root)
+
+
+# ----------------------------------------------------------------------------------------------
+# FRI commit chain
+# ----------------------------------------------------------------------------------------------
+def assert_fri_equal(O, fid, proto, want):
+    assert proto.get_roots() == want.roots()
+    assert np.array_equal(proto.challenges, want.challenges)
+    assert proto.get_final_root() == want.final_root
+    assert np.array_equal(proto.final_coefficients, want.final_coefficients)
+    assert np.array_equal(proto.l0_commitment.nodes, want.l0_nodes)
+    for i, v in enumerate(proto.intermediate_values):
+        assert np.array_equal(v.as_ref(), want.layer_values[i]), f"layer {i} values"
+        assert np.array_equal(proto.intermediate_commitments[i].nodes, want.layer_nodes[i]), f"layer {i} nodes"
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_fri_commit_matches_oracle(hodor, oracle, fid):
+    """proof_from_lde_by_values on random values (the commit chain is defined for any input)."""
+    for log_n, L, oc in [(2, 2, 1), (4, 4, 2), (6, 2, 1), (10, 8, 1), (12, 16, 4), (14, 8, 1), (16, 16, 1)]:
+        v = oracle.random_elements(fid, 1 << log_n, seed=900 + log_n)
+        proto = hodor.NaiveFriIop.proof_from_lde(hodor.Polynomial.from_values(fid, v), L, oc, hodor.Worker())
+        assert_fri_equal(oracle, fid, proto, oracle.fri_commit(fid, v, L, oc))
+
+
+def test_fri_host_signature_matches_oracle(hodor, oracle):
+    """The reference-shaped entry point (everything copied to caller buffers)."""
+    from hodor_b200 import _ffi
+    from hodor_b200._ffi import u8p, u64p
+    from hodor_b200.field import _p
+    fid, log_n, L, oc = 0, 12, 8, 2
+    n = 1 << log_n
+    v = oracle.random_elements(fid, n, seed=1234)
+    steps = oracle.fri_num_steps(n, L, oc)
+    l0 = np.zeros((n, 32), np.uint8)
+    ln = [np.zeros((n >> (i + 1), 32), np.uint8) for i in range(steps)]
+    lv = [np.zeros((n >> (i + 1), 4), np.uint64) for i in range(steps)]
+    ch = np.zeros((steps, 4), np.uint64)
+    fr = np.zeros(32, np.uint8)
+    fc = np.zeros((oc, 4), np.uint64)
+    lnp = (u8p * steps)(*[a.ctypes.data_as(u8p) for a in ln])
+    lvp = (u64p * steps)(*[_p(a) for a in lv])
+    rc = _ffi.lib.hodor_cuda_fri_commit_host(_p(v), C.c_uint64(n), L, oc, l0.ctypes.data_as(u8p), lnp, lvp, _p(ch),
+                                             fr.ctypes.data_as(u8p), _p(fc), fid)
+    assert rc == steps, _ffi.last_error()
+    want = oracle.fri_commit(fid, v, L, oc)
+    assert np.array_equal(l0, want.l0_nodes) and np.array_equal(ch, want.challenges)
+    assert fr.tobytes() == want.final_root and np.array_equal(fc, want.final_coefficients)
+    for i in range(steps):
+        assert np.array_equal(ln[i], want.layer_nodes[i]) and np.array_equal(lv[i], want.layer_values[i])
+
+
+def test_one_fri_step_shape_and_low_degree(hodor, oracle):
+    """test_one_fri_step (src/fri/mod.rs:252-331) over bn256.rs's field: coefficients 1, 2, 4, 8,
+    lde_factor 4, output 2; the fold must equal the LDE of (a0 + c a1, a2 + c a3)."""
+    from hodor_b200 import field as f
+    fid = 0
+    coeffs = oracle.to_mont(fid, oracle.ints_to_array([1, 2, 4, 8]))
+    lde_values = hodor.Polynomial.from_coeffs(fid, coeffs).lde(hodor.Worker(), 4)
+    proto = hodor.NaiveFriIop.proof_from_lde_by_values(lde_values, 4, 2, hodor.Worker())
+    c = proto.challenges[0]
+    new_coeffs = np.stack([f.add(fid, coeffs[0], f.mul(fid, c, coeffs[1])), f.add(fid, coeffs[2], f.mul(fid, c, coeffs[3]))])
+    assert np.array_equal(proto.final_coefficients, new_coeffs)
+    next_lde = hodor.Polynomial.from_coeffs(fid, new_coeffs).lde(hodor.Worker(), 4)
+    assert np.array_equal(proto.intermediate_values[0].as_ref(), next_lde.as_ref())
+    assert proto.intermediate_commitments[0] == hodor.TrivialBlake2sIOP.create(fid, next_lde.as_ref())
+    # query production (src/fri/query_producer.rs): every query verifies against its layer's root
+    for start in (1, 3, 7, 12):
+        proof = hodor.NaiveFriIop.prototype_into_proof(proto, lde_values, start)
+        assert len(proof.queries) == 2 * len(proof.roots)
+        for k, q in enumerate(proof.queries):
+            assert hodor.TrivialBlake2sIOP.verify_query(q, proof.roots[k // 2])
+
+
+def test_fri_argument_errors(hodor, oracle):
+    v = hodor.Polynomial.from_values(0, oracle.random_elements(0, 16, 1))
+    with pytest.raises(hodor.HodorError):
+        hodor.NaiveFriIop.proof_from_lde(v, 16, 1, None)  # zero folding steps: the reference panics
+    with pytest.raises(hodor.HodorError):
+        hodor.NaiveFriIop.proof_from_lde(v, 3, 1, None)  # assert!(lde_factor.is_power_of_two())
+
+
+def test_fri_chain_2p24_properties(hodor, oracle):
+    """BASELINE.json configs[2] at full size: N = 2^24, blowup 8, one output coefficient (21 layers).
+    Size-independent checks: (a) every challenge is interpret_hash of the previous root; (b) sampled
+    fold outputs recomputed on the host from the layer below; (c) every query of a produced proof
+    verifies; (d) the first three and last three layers are bit-exact against the CPU oracle run on
+    those layers' inputs; (e) final coefficient == iNTT of the last layer."""
+    from hodor_b200 import field as f
+    fid, log_n, L, oc = 0, 24, 8, 1
+    n = 1 << log_n
+    v = oracle.random_elements(fid, n, seed=777)
+    proto = hodor.NaiveFriIop.proof_from_lde(hodor.Polynomial.from_values(fid, v), L, oc, None)
+    steps = proto.num_steps
+    assert steps == 21
+    roots = proto.get_roots()
+    for i in range(steps):
+        assert np.array_equal(proto.challenges[i], oracle.interpret_hash(fid, roots[i]))
+    winv = oracle.inverse(fid, oracle.domain_generator(fid, log_n))
+    two_inv = oracle.inverse(fid, oracle.to_mont(fid, oracle.ints_to_array([2]))[0])
+    rng = np.random.default_rng(3)
+    values = [v] + [p.as_ref() for p in proto.intermediate_values]
+    for i in range(steps):
+        half = n >> (i + 1)
+        for idx in {0, half - 1, *[int(x) for x in rng.integers(0, half, 3)]}:
+            f0, f1 = values[i][idx], values[i][idx + half]
+            odd = f.mul(fid, f.sub(fid, f0, f1), oracle.pow_(fid, winv, idx << i))
+            want = f.mul(fid, f.add(fid, f.mul(fid, odd, proto.challenges[i]), f.add(fid, f0, f1)), two_inv)
+            assert np.array_equal(values[i + 1][idx], want), (i, idx)
+    for layer in (1, 2, steps - 2, steps - 1, steps):
+        assert np.array_equal(proto.intermediate_commitments[layer - 1].nodes, oracle.merkle_create(fid, values[layer]))
+    small = oracle.fri_commit(fid, values[steps - 3], L, oc)  # the last three folds as their own chain
+    assert small.roots()[1:] == roots[steps - 2 :]
+    assert np.array_equal(proto.final_coefficients, oracle.ifft(fid, values[steps], 3)[:oc])
+    proof = proto.produce_proof(None, 123457)
+    for k, q in enumerate(proof.queries):
+        assert hodor.TrivialBlake2sIOP.verify_query(q, proof.roots[k // 2])
+
+
+# ----------------------------------------------------------------------------------------------
+# device-pointer entry points
+# ----------------------------------------------------------------------------------------------
+def test_device_entry_points(hodor, oracle):
+    import torch
+    from hodor_b200 import device as dev
+    fid, log_n, L = 0, 14, 8
+    n = 1 << log_n
+    a = oracle.random_elements(fid, n, seed=66)
+    d_a = dev.to_device(a)
+    d_out = dev.empty_elems(n * L)
+    dev.lde(d_a, log_n, 3, True, d_out, fid)
+    want = oracle.lde(fid, a, log_n, L, True)
+    assert np.array_equal(dev.to_host(d_out), want)
+    d_nodes = torch.empty((n * L, 4), dtype=torch.int64, device="cuda")
+    d_root = torch.empty(4, dtype=torch.int64, device="cuda")
+    d_chal = torch.empty(4, dtype=torch.int64, device="cuda")
+    dev.merkle_build(d_out, n * L, d_nodes, fid, d_root, d_chal)
+    nodes = oracle.merkle_create(fid, want)
+    assert np.array_equal(d_nodes.cpu().numpy().view(np.uint8).reshape(-1, 32), nodes)
+    assert d_root.cpu().numpy().tobytes() == nodes[1].tobytes()
+    assert np.array_equal(d_chal.cpu().numpy().view(np.uint64), oracle.interpret_hash(fid, nodes[1].tobytes()))
+    d_next = dev.empty_elems(n * L // 2)
+    dev.fri_fold(d_out, n * L, n * L, 0, d_chal, d_next, fid)
+    assert np.array_equal(dev.to_host(d_next), oracle.fri_commit(fid, want, L, 1).layer_values[0])
+    # in place forward / inverse on the device
+    d_b = dev.to_device(a)
+    dev.fft(d_b, d_b, log_n, False, fid)
+    assert np.array_equal(dev.to_host(d_b), oracle.fft(fid, a, log_n))
+    dev.ifft(d_b, d_b, log_n, False, fid)
+    assert np.array_equal(dev.to_host(d_b), a)
+    proto = dev.fri_commit(d_out, L, 1, fid)
+    assert proto.get_roots() == oracle.fri_commit(fid, want, L, 1).roots()
+    assert dev.launch_count() > 0
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharded_steps_single_gpu(hodor, oracle, world):
+    """The two local steps of the four-step NTT, with the all-to-all emulated on one GPU: all
+    `world` ranks' slices are processed in turn.  (The NCCL path is exercised by bench.py.)"""
+    import torch
+    from hodor_b200 import device as dev
+    from hodor_b200.sharded import CudaBackend, gather_output, scatter_input
+    fid, log_n = 0, 16
+    log_g = world.bit_length() - 1
+    a = oracle.random_elements(fid, 1 << log_n, seed=55)
+    omega = oracle.domain_generator(fid, log_n)
+    be = CudaBackend()
+    cols = [be.shard_cols(dev.to_device(scatter_input(a, world, g)), log_n, log_g, g, omega, fid) for g in range(world)]
+    m = (1 << log_n) // world
+    chunk = m // world
+    outs = []
+    for h in range(world):
+        recv = torch.cat([cols[g][h * chunk : (h + 1) * chunk] for g in range(world)]).contiguous()
+        outs.append(dev.to_host(be.shard_rows(recv, log_n, log_g, h, omega, fid)))
+    assert np.array_equal(gather_output(outs), oracle.serial_fft(fid, a, omega, log_n))

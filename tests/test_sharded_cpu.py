@@ -1,0 +1,92 @@
+"""world_size-2 (and 4) gloo test of the multi-GPU host logic in hodor_b200/sharded.py: the
+distribution contract (scatter_input / gather_output) and the all-to-all plumbing of the four-step
+NTT.  The two local compute steps are injected from the CPU oracle here, because this box has no
+GPU; on the GPU box the same orchestration runs with CudaBackend (tests/test_gpu_parity.py checks
+those kernels, bench.py runs the NCCL path)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    """Test double for the two CUDA steps (TEST ONLY: uses oracle/)."""
+
+    def __init__(self):
+        from oracle import oracle as O
+        self.O = O
+
+    def shard_cols(self, src, log_n, log_g, rank, omega, field_id):
+        O = self.O
+        a = src.numpy().view(np.uint64)
+        m = a.shape[0]
+        wm = O.pow_(field_id, omega, 1 << log_g)
+        b = O.serial_fft(field_id, a, wm, log_n - log_g)
+        b = O.distribute_powers(field_id, b, O.pow_(field_id, omega, rank), cpus=1)
+        assert b.shape[0] == m
+        return torch.from_numpy(b.view(np.int64))
+
+    def shard_rows(self, src, log_n, log_g, rank, omega, field_id):
+        O = self.O
+        G = 1 << log_g
+        mat = src.numpy().view(np.uint64).reshape(G, -1, 4)
+        cols = mat.shape[1]
+        wg = O.pow_(field_id, omega, (1 << log_n) >> log_g)
+        out = np.zeros_like(mat)
+        for k in range(cols):
+            out[:, k, :] = O.serial_fft(field_id, np.ascontiguousarray(mat[:, k, :]), wg, log_g)
+        return torch.from_numpy(out.reshape(-1, 4).view(np.int64))
+
+
+def _worker(rank, world, port, log_n, field_id, result_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hodor_b200.sharded import ntt_sharded, scatter_input
+        from oracle import oracle as O
+        a = O.random_elements(field_id, 1 << log_n, seed=4321)
+        omega = O.domain_generator(field_id, log_n)
+        local = torch.from_numpy(scatter_input(a, world, rank).view(np.int64))
+        out = ntt_sharded(local, log_n, omega, field_id, backend=OracleBackend())
+        np.save(os.path.join(result_dir, f"out{rank}.npy"), out.numpy().view(np.uint64))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 8), (4, 9)])
+def test_four_step_over_gloo(oracle, tmp_path, world, log_n):
+    from hodor_b200.sharded import gather_output
+    field_id = 0
+    mp.spawn(_worker, args=(world, _free_port(), log_n, field_id, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"out{r}.npy") for r in range(world)]
+    a = oracle.random_elements(field_id, 1 << log_n, seed=4321)
+    want = oracle.serial_fft(field_id, a, oracle.domain_generator(field_id, log_n), log_n)
+    assert np.array_equal(gather_output(parts), want)
+
+
+def test_sharded_argument_checks():
+    from hodor_b200.sharded import gather_output, ntt_sharded, scatter_input
+    a = np.arange(64, dtype=np.uint64).reshape(16, 4)
+    assert np.array_equal(scatter_input(a, 4, 1), a[1::4])
+    parts = [np.full((4, 4), h, np.uint64) for h in range(2)]
+    g = gather_output(parts)  # m = 4, chunk = 2: [h0 h0 h1 h1 | h0 h0 h1 h1]
+    assert [int(x) for x in g[:, 0]] == [0, 0, 1, 1, 0, 0, 1, 1]
+    with pytest.raises(ValueError):
+        ntt_sharded(torch.zeros((3, 4), dtype=torch.int64), 4, np.zeros(4, np.uint64), 0, backend=OracleBackend())
