@@ -281,7 +281,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     def fri_step():
         proto = dev.fri_commit(d_vals, FRI_L, FRI_OUT, FIELD)
-        del proto
+        proto.free()
 
     for _ in range(max(1, args.warmup - 1)):
         fri_step()

@@ -57,6 +57,47 @@ int Ctx::ensure_io(int which, size_t bytes) {
     return HODOR_OK;
 }
 
+// Size-bucketed cache of device blocks for objects with caller-controlled lifetime (FRI
+// prototypes): a prover commits chain after chain of the same size, so steady state makes no
+// driver allocation calls.  Blocks are only recycled after the owner synchronised its stream.
+void* Ctx::pool_alloc(size_t bytes) {
+    for (size_t i = 0; i < pool_free_list.size(); i++) {
+        if (pool_free_list[i].second >= bytes && pool_free_list[i].second <= bytes + bytes / 4) {
+            void* p = pool_free_list[i].first;
+            pool_live[p] = pool_free_list[i].second;
+            pool_free_list.erase(pool_free_list.begin() + i);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {  // drop the cache and retry once
+        cudaGetLastError();
+        for (auto& b : pool_free_list) cudaFree(b.first);
+        pool_free_list.clear();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMalloc(pool)");
+        return nullptr;
+    }
+    pool_live[p] = bytes;
+    return p;
+}
+void Ctx::pool_free(void* p) {
+    auto it = pool_live.find(p);
+    if (it == pool_live.end()) {
+        cudaFree(p);
+        return;
+    }
+    const size_t bytes = it->second;
+    pool_live.erase(it);
+    size_t cached = 0;
+    for (auto& b : pool_free_list) cached += b.second;
+    if (pool_free_list.size() >= 8 || cached + bytes > ((size_t)16 << 30)) cudaFree(p);
+    else pool_free_list.emplace_back(p, bytes);
+}
+
 cudaEvent_t Ctx::take_event() {
     if (!event_pool.empty()) {
         cudaEvent_t e = event_pool.back();
@@ -217,6 +258,7 @@ void hodor_cuda_shutdown(void) {
     if (g_ctx->ws) cudaFree(g_ctx->ws);
     for (int i = 0; i < 2; i++)
         if (g_ctx->io[i]) cudaFree(g_ctx->io[i]);
+    for (auto& b : g_ctx->pool_free_list) cudaFree(b.first);
     for (auto& r : g_ctx->prof) {
         cudaEventDestroy(r.start);
         cudaEventDestroy(r.stop);
@@ -350,7 +392,12 @@ void* hodor_cuda_host_alloc(size_t bytes) {
 void hodor_cuda_host_free(void* hptr) {
     if (hptr) cudaFreeHost(hptr);
 }
-static cudaStream_t pick_stream(Ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
+// The caller's stream handle is used verbatim: NULL is CUDA's legacy default stream (what
+// torch.cuda.current_stream().cuda_stream returns for the default stream), not the library's own.
+static cudaStream_t pick_stream(Ctx* c, void* stream) {
+    (void)c;
+    return (cudaStream_t)stream;
+}
 int hodor_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream) {
     Ctx* c = ctx();
     if (!c) return HODOR_ERR_CUDA;
@@ -607,8 +654,9 @@ struct hodor_fri_proto {
 
 static void fri_destroy(hodor_fri_proto* p) {
     if (!p) return;
-    if (p->block) cudaFree(p->block);
-    if (p->owned_lde) cudaFree(p->owned_lde);
+    Ctx* c = g_ctx;
+    if (p->block) c ? c->pool_free(p->block) : (void)cudaFree(p->block);
+    if (p->owned_lde) c ? c->pool_free(p->owned_lde) : (void)cudaFree(p->owned_lde);
     delete p;
 }
 
@@ -645,10 +693,8 @@ hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t
     if (lde_on_device) {
         p->lde = (const uint4*)lde;
     } else {
-        if (cudaMalloc((void**)&p->owned_lde, n * 32) != cudaSuccess) {
-            cuda_fail(cudaGetLastError(), "cudaMalloc(lde)");
-            return nullptr;
-        }
+        p->owned_lde = (uint4*)c->pool_alloc(n * 32);
+        if (!p->owned_lde) return nullptr;
         if (cudaMemcpyAsync(p->owned_lde, lde, n * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) {
             cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(lde)");
             return nullptr;
@@ -660,10 +706,8 @@ hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t
     for (int i = 0; i < steps; i++) slots += 2 * (n >> (i + 1));
     const size_t last = n >> steps;
     slots += 2 * (size_t)(steps + 1) + last + 80;
-    if (cudaMalloc((void**)&p->block, slots * 32) != cudaSuccess) {
-        cuda_fail(cudaGetLastError(), "cudaMalloc(fri)");
-        return nullptr;
-    }
+    p->block = (uint4*)c->pool_alloc(slots * 32);
+    if (!p->block) return nullptr;
     uint4* cur = p->block;
     auto take = [&](size_t count) {
         uint4* r = cur;

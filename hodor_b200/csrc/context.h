@@ -73,6 +73,11 @@ struct Ctx {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> event_pool;
 
+    std::vector<std::pair<void*, size_t>> pool_free_list;
+    std::map<void*, size_t> pool_live;
+    void* pool_alloc(size_t bytes);
+    void pool_free(void* p);
+
     int ensure_workspace(size_t bytes);
     int ensure_io(int which, size_t bytes);
     cudaEvent_t take_event();

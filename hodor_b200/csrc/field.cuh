@@ -273,14 +273,20 @@ HD uint32_t sub256(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)
 // ---------------------------------------------------------------------------------------------
 template <class F>
 struct Field {
-    // The modulus lives in vector registers: ptxas only fuses mad.lo.cc/madc.hi.cc pairs into
-    // IMAD.WIDE.U32.X when both factors are registers.  `opaque_zero` must be 0 at run time but
-    // unknown (and per-thread) at compile time, e.g. threadIdx.x & kernel_param_zero; with the
-    // default 0 the limbs constant-fold into immediates.
+    // Where the modulus lives.  ptxas fuses a mad.lo.cc/madc.hi.cc pair into one IMAD.WIDE.U32.X only
+    // when both factors are vector registers; with an immediate (or uniform-register) factor it
+    // emits IMAD.X + IMAD.HI.U32.X.  Measured on B200 (tools/microbench.cu, profiles/): IMAD.WIDE
+    // issues at half the IMAD rate, so both forms cost the same multiplier time (58.8 vs 56.8
+    // Gmul/s in favour of immediates) and the immediate form saves 8 registers per thread.  Define
+    // HODOR_MODULUS_IN_REGS=1 to keep the modulus in registers: `opaque_zero` must then be 0 at run
+    // time but unknown and per-thread at compile time (threadIdx.x & kernel_param_zero).
+#ifndef HODOR_MODULUS_IN_REGS
+#define HODOR_MODULUS_IN_REGS 0
+#endif
     uint32_t p[8];
     HD explicit Field(uint32_t opaque_zero = 0) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) p[i] = F::P(i) | opaque_zero;
+        for (int i = 0; i < 8; i++) p[i] = F::P(i) | (HODOR_MODULUS_IN_REGS ? opaque_zero : 0u);
     }
 
     HD static Fe one() {

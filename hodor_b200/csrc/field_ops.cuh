@@ -247,6 +247,8 @@ struct Ops {
         static bool configured = false;  // guarded by Ctx::mu
         if (!configured) {
             HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                cudaSharedmemCarveoutMaxShared));
             configured = true;
         }
         {
@@ -467,10 +469,17 @@ struct Ops {
                         cudaStream_t st) {
         // omega_N^-1 of the INITIAL domain (src/fri/fri_on_values.rs:24-25), table over exponents < N/2
         maybe_evict(c);
+        static std::map<uint32_t, Fe> inv_cache;  // guarded by Ctx::mu; a host inversion is ~400 host multiplies
         Fe omega, omega_inv;
         int rc = h_domain_generator(log_n0, omega);
         if (rc) return fail(rc, "FRI domain larger than the field's 2-adicity");
-        h_inverse(omega, omega_inv);
+        auto cached = inv_cache.find(log_n0);
+        if (cached == inv_cache.end()) {
+            h_inverse(omega, omega_inv);
+            inv_cache.emplace(log_n0, omega_inv);
+        } else {
+            omega_inv = cached->second;
+        }
         const PowTables* t = nullptr;
         std::vector<Fe> bases{omega_inv};
         rc = get_pow_tables(c, &t, bases, log_n0 > 1 ? log_n0 - 1 : 1, nullptr, st);

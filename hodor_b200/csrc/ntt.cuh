@@ -78,11 +78,12 @@ DEV void sts_fe(uint4* sm, uint32_t plane, uint32_t slot, const Fe& r) {
     sm[slot] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
     sm[plane + slot] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
-// copy a kernel-parameter (constant bank) element into vector registers
+// a kernel-parameter (constant bank) element as a multiplier operand; see Field<F>::Field on why
+// it is not forced into vector registers by default
 DEV Fe ld_param(const Fe& c, uint32_t opaque_zero) {
     Fe r;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = c.v[i] | opaque_zero;
+    for (int i = 0; i < 8; i++) r.v[i] = c.v[i] | (HODOR_MODULUS_IN_REGS ? opaque_zero : 0u);
     return r;
 }
 
@@ -180,8 +181,16 @@ DEV uint32_t local_out_index(uint32_t pos) {
     return k1 | (k2 << R1) | (k3 << (R1 + R2));
 }
 
+// Resident blocks per SM the pass kernel is compiled for: 2^B threads x 8 elements in registers.
+// B = 8 (the 2^24 workhorse): 2 x 256 threads at <= 128 registers and 2 x 64 KiB of shared memory,
+// so one block's global loads / barrier waits overlap the other's multiplier work.
+template <int B>
+struct PassOccupancy {
+    static constexpr int MIN_BLOCKS = B >= 9 ? 1 : (B == 8 ? 2 : (B == 7 ? 4 : 8));
+};
+
 template <class F, int B, bool SCALE_IN, bool LAST>
-__global__ void __launch_bounds__(1 << B) ntt_pass_kernel(const __grid_constant__ NttPass p) {
+__global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass_kernel(const __grid_constant__ NttPass p) {
     using G = Groups<B>;
     extern __shared__ uint4 sm[];
     const uint32_t tid = threadIdx.x;

@@ -58,10 +58,14 @@ class FRIProofPrototype:
                                          for i in range(steps)]
         self._values: List[Optional[Polynomial]] = [None] * steps
 
-    def __del__(self):
+    def free(self) -> None:
+        """Return the prototype's device memory (trees, layer values) to the library."""
         h, self._handle = getattr(self, "_handle", None), None
         if h:
             lib.hodor_cuda_fri_free(h)
+
+    def __del__(self):
+        self.free()
 
     # FriProofPrototype trait (:26-30, :119-138)
     def get_roots(self) -> List[bytes]:

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -225,11 +226,17 @@ class DeviceIOP:
 
     def __init__(self, field_id: int, proto, layer: int, size: int, root: bytes):
         self.field_id = field_id
-        self._proto = proto
+        self._proto_ref = weakref.ref(proto)  # no cycle: dropping the prototype frees its HBM at once
         self._layer = layer
         self._size = size
         self._root = root
         self._nodes: Optional[np.ndarray] = None
+
+    def _proto(self):
+        proto = self._proto_ref()
+        if proto is None or not proto._handle:
+            raise RuntimeError("the FRIProofPrototype that owns this commitment's device memory was freed")
+        return proto
 
     def size(self) -> int:
         return self._size
@@ -243,12 +250,12 @@ class DeviceIOP:
     @property
     def nodes(self) -> np.ndarray:
         if self._nodes is None:
-            self._nodes = self._proto._fetch_layer(self._layer, want_nodes=True)[0]
+            self._nodes = self._proto()._fetch_layer(self._layer, want_nodes=True)[0]
         return self._nodes
 
     def query(self, natural_index: int, leafs=None) -> TrivialBlake2sIopQuery:
         assert natural_index < self._size
-        return self._proto._query(self._layer, natural_index)
+        return self._proto()._query(self._layer, natural_index)
 
     verify_query = staticmethod(TrivialBlake2sIOP.verify_query)
 
