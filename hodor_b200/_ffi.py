@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhodor_b200.so")
+LIB_PATH = os.environ.get("HODOR_B200_LIB") or os.path.join(_HERE, "libhodor_b200.so")  # override: A/B builds
 
 OK = 0
 ERR_INVALID_ARG = -1

@@ -149,6 +149,59 @@ HD void row_mad_nocarry(uint32_t (&acc)[8], uint32_t x0, uint32_t x2, uint32_t x
 #endif
 }
 
+// Reduction rows for moduli with p0 = 1, p1 = 0xffffffff (BLS12-381 Fr, i.e. src/bn256.rs): the two
+// low products are additions.  m*p0 = m: (acc0, acc1) += m, which zeroes acc0 (m = -acc0).
+HD void row_mad_p0_one(uint32_t (&acc)[8], uint32_t x2, uint32_t x4, uint32_t x6, uint32_t m, uint32_t& top) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32      %0, %0, %12;\n\t"
+        "addc.cc.u32     %1, %1, 0;\n\t"
+        "madc.lo.cc.u32  %2, %9,  %12, %2;\n\t"
+        "madc.hi.cc.u32  %3, %9,  %12, %3;\n\t"
+        "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32  %6, %11, %12, %6;\n\t"
+        "madc.hi.cc.u32  %7, %11, %12, %7;\n\t"
+        "addc.u32        %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(top)
+        : "r"(x2), "r"(x4), "r"(x6), "r"(m));
+#else
+    row_mad(acc, 1u, x2, x4, x6, m, top);
+#endif
+}
+// m*p1 = m*(2^32 - 1): low word lo1 = -m, high word hi1 = m - (m != 0); carry out provably zero
+HD void row_mad_p1_ones(uint32_t (&acc)[8], uint32_t lo1, uint32_t hi1, uint32_t x3, uint32_t x5, uint32_t x7,
+                        uint32_t m) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32      %0, %0, %8;\n\t"
+        "addc.cc.u32     %1, %1, %9;\n\t"
+        "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.u32     %7, %12, %13, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7])
+        : "r"(lo1), "r"(hi1), "r"(x3), "r"(x5), "r"(x7), "r"(m));
+#else
+    uint64_t s = (uint64_t)acc[0] + lo1;
+    acc[0] = (uint32_t)s;
+    s = (uint64_t)acc[1] + hi1 + (s >> 32);
+    acc[1] = (uint32_t)s;
+    uint64_t c = s >> 32;
+    const uint32_t x[3] = {x3, x5, x7};
+    for (int k = 0; k < 3; k++) {
+        const uint64_t prod = (uint64_t)x[k] * m;
+        const uint64_t lo = (uint64_t)acc[2 * k + 2] + (uint32_t)prod + c;
+        acc[2 * k + 2] = (uint32_t)lo;
+        const uint64_t hi = (uint64_t)acc[2 * k + 3] + (prod >> 32) + (lo >> 32);
+        acc[2 * k + 3] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+#endif
+}
+
 // acc[0..7] = x0*y, x2*y<<64, ... (no accumulate, no carries)
 HD void row_mul(uint32_t (&acc)[8], uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
 #ifdef __CUDA_ARCH__
@@ -268,6 +321,10 @@ HD uint32_t sub256(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)
     return borrow;
 }
 
+}  // namespace hodor
+#include "mont_split.cuh"
+namespace hodor {
+
 // ---------------------------------------------------------------------------------------------
 // Field<F>: canonical Montgomery arithmetic
 // ---------------------------------------------------------------------------------------------
@@ -358,31 +415,116 @@ struct Field {
     // two arrays trade roles each step.  Carries out of the low-aligned accumulator (weight 2^256)
     // are exactly one unit of word 7 of the offset accumulator.  The offset accumulator cannot
     // overflow: T + a*y + m*p < (2 + 2^33) p < 2^288 for every p < 0.49 * 2^256.
-    HD Fe mul(const Fe& a, const Fe& b) const {
+    //
+    // Code size: the inlined body is ~300 SASS instructions, so a pass kernel with ~60 multiplies is
+    // 200-280 KB of straight-line code and ncu shows ~20 % `no_instruction` stall samples.  An
+    // out-of-line copy (HODOR_MUL_OUT_OF_LINE=1: static, by value, operands in registers) shrinks
+    // the kernels to ~50 KB but measured 10 % SLOWER on the 2^24 LDE (45.0 vs 40.9 ms, call and
+    // register-shuffle overhead; profiles/r01_experiments.md), so inlining stays the default.
+#ifndef HODOR_MUL_OUT_OF_LINE
+#define HODOR_MUL_OUT_OF_LINE 0
+#endif
+#if defined(__CUDA_ARCH__) && HODOR_MUL_OUT_OF_LINE && !HODOR_MODULUS_IN_REGS
+    static __device__ __noinline__ Fe mul_out_of_line(Fe a, Fe b) { return Field<F>().mul_inline(a, b); }
+    DEV Fe mul(const Fe& a, const Fe& b) const { return mul_out_of_line(a, b); }
+#else
+    HD Fe mul(const Fe& a, const Fe& b) const { return mul_inline(a, b); }
+#endif
+
+    // Which multiplier: 0 = even/odd carry-save (default), 1 = split lo/hi chains (mont_split.cuh;
+    // measured slower: ptxas has to emit IMAD + IADD3.X per term because IMAD has no carry out).
+#ifndef HODOR_MUL_SPLIT
+#define HODOR_MUL_SPLIT 0
+#endif
+    HD Fe mul_inline(const Fe& a, const Fe& b) const {
+#if HODOR_MUL_SPLIT
+        return mul_split(a, b);
+#else
+        return mul_evenodd(a, b);
+#endif
+    }
+
+    // Product by rows with separate low / high carry chains, then word-serial reduction; see
+    // mont_split.cuh for the cost model and the overflow argument.
+    // Short-cut reduction rows for p0 = 1, p1 = 0xffffffff (reduce_round below).  Measured on B200 in the
+    // same session: the isolated multiplier gains 10 % (58.5 -> 64.2 Gmul/s) but the 2^24 LDE LOSES
+    // 6 % (40.8 -> 43.2 ms): the extra dependent ALU instructions and registers (spills at the
+    // 128-register cap) cost more than the 16 saved products.  Off by default.
+#ifndef HODOR_USE_P01
+#define HODOR_USE_P01 0
+#endif
+    static constexpr bool P01 = HODOR_USE_P01 && F::P(0) == 1u && F::P(1) == 0xffffffffu && F::INV == 0xffffffffu;
+    HD Fe mul_split(const Fe& a, const Fe& b) const {
+        uint32_t T[16], cy[9];
+#pragma unroll
+        for (int i = 9; i < 16; i++) T[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) cy[i] = 0;
+        sp_row0_lo(T, a.v, b.v[0]);
+        sp_row0_hi(T, a.v, b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            sp_row_lo(T + i, a.v, b.v[i]);
+            sp_row_hi(T + i, a.v, b.v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if constexpr (P01) {
+                const uint32_t m = 0u - T[i];
+                const uint32_t hi1 = m - (m != 0u ? 1u : 0u);
+                sp_red_lo_p01(T + i, cy[i], m, p);
+                sp_red_hi_p01(T + i, cy[i + 1], hi1, m, p);
+            } else {
+                const uint32_t m = T[i] * F::INV;
+                sp_red_lo(T + i, cy[i], m, p);
+                sp_red_hi(T + i, cy[i + 1], m, p);
+            }
+        }
+        Fe r;
+        uint32_t hi[8], c8[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            hi[i] = T[8 + i];
+            c8[i] = cy[i];  // cy[8] == 0: nothing can leave word 15
+        }
+        add256(r.v, hi, c8);
+        reduce_once(r.v);
+        return r;
+    }
+
+    // One reduction round: low += m*p (even limbs of p), off += m*p (odd limbs), m = -low[0]/p mod 2^32.
+    // For p0 = 1, p1 = 0xffffffff the two low products are additions and m is a negation.
+    HD void reduce_round(uint32_t (&low)[8], uint32_t (&off)[8]) const {
+        if constexpr (P01) {
+            const uint32_t t0 = low[0];
+            const uint32_t m = 0u - t0;
+            const uint32_t hi1 = m - (m != 0u ? 1u : 0u);
+            row_mad_p1_ones(off, t0, hi1, p[3], p[5], p[7], m);
+            row_mad_p0_one(low, p[2], p[4], p[6], m, off[7]);
+        } else {
+            const uint32_t m = low[0] * F::INV;
+            row_mad_nocarry(off, p[1], p[3], p[5], p[7], m);
+            row_mad(low, p[0], p[2], p[4], p[6], m, off[7]);
+        }
+    }
+
+    HD Fe mul_evenodd(const Fe& a, const Fe& b) const {
         uint32_t even[8], odd[8];
         // step 0
         row_mul(even, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
         row_mul(odd, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
-        {
-            uint32_t m = even[0] * F::INV;
-            row_mad_nocarry(odd, p[1], p[3], p[5], p[7], m);
-            row_mad(even, p[0], p[2], p[4], p[6], m, odd[7]);
-        }
+        reduce_round(even, odd);
 #pragma unroll
         for (int i = 1; i < 8; i += 2) {
             {  // odd step: `odd` is low-aligned, `even` is shifted
                 row_shift_mad(odd, even, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
                 row_mad(odd, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], even[7]);
-                uint32_t m = odd[0] * F::INV;
-                row_mad_nocarry(even, p[1], p[3], p[5], p[7], m);
-                row_mad(odd, p[0], p[2], p[4], p[6], m, even[7]);
+                reduce_round(odd, even);
             }
             if (i + 1 < 8) {  // even step: roles back
                 row_shift_mad(even, odd, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
                 row_mad(even, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], odd[7]);
-                uint32_t m = even[0] * F::INV;
-                row_mad_nocarry(odd, p[1], p[3], p[5], p[7], m);
-                row_mad(even, p[0], p[2], p[4], p[6], m, odd[7]);
+                reduce_round(even, odd);
             }
         }
         // after step 7: low-aligned = odd (word 0 == 0), offset = even.  T = (odd >> 32) + even.

@@ -7,7 +7,8 @@
 #include "../hodor_b200/csrc/merkle.cuh"
 using namespace hodor;
 
-template <class F, int ILP, bool REGS>
+// REGS: modulus in vector registers (IMAD.WIDE everywhere) vs immediates; SPLIT: mont_split.cuh
+template <class F, int ILP, bool REGS, bool SPLIT = false>
 __global__ void __launch_bounds__(256) mul_kernel(const Fe* in, Fe* out, int iters, uint32_t zero) {
     const Field<F> fld(REGS ? (threadIdx.x & zero) : 0u);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -17,7 +18,7 @@ __global__ void __launch_bounds__(256) mul_kernel(const Fe* in, Fe* out, int ite
     for (int j = 0; j < ILP; j++) x[j] = in[(tid + 7 * j) & 1023];
     for (int k = 0; k < iters; k++) {
 #pragma unroll
-        for (int j = 0; j < ILP; j++) x[j] = fld.mul(x[j], y);
+        for (int j = 0; j < ILP; j++) x[j] = SPLIT ? fld.mul_split(x[j], y) : fld.mul_evenodd(x[j], y);
     }
     Fe acc = x[0];
 #pragma unroll
@@ -96,6 +97,12 @@ int main() {
                ILP, (int)REGS, bps, threads * iters * ILP / ms / 1e6);                                      \
     }
         RUN_MUL(BlsFr, 1, false, "mont_mul_bls")
+        {
+            double ms = time_ms(mul_kernel<BlsFr, 1, false, true>, grid, block, (const Fe*)d_in, d_out, iters, 0u);
+            printf("{\"bench\": \"mont_mul_bls_split\", \"blocks_per_sm\": %d, \"gmul_per_s\": %.2f}\n", bps, threads * iters / ms / 1e6);
+            ms = time_ms(mul_kernel<Bn254Fr, 1, false, true>, grid, block, (const Fe*)d_in, d_out, iters, 0u);
+            printf("{\"bench\": \"mont_mul_bn254_split\", \"blocks_per_sm\": %d, \"gmul_per_s\": %.2f}\n", bps, threads * iters / ms / 1e6);
+        }
         RUN_MUL(BlsFr, 1, true, "mont_mul_bls")
         RUN_MUL(BlsFr, 2, true, "mont_mul_bls")
         RUN_MUL(BlsFr, 4, true, "mont_mul_bls")
