@@ -41,6 +41,15 @@ FRI_OUT = 1
 P_TOP_LIMB = 0x73EDA753299D7D48  # top u64 limb of the modulus: any element with a smaller top limb is canonical
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -175,7 +184,7 @@ def run_reference(args, rank: int):
                 "sample": f"FRI commit chain on 2^20 values, blowup {FRI_L}, {cores} cores, {fri_dt:.2f} s"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -382,7 +391,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             line["sharded_ntt"] = {"collective": "NCCL all_to_all_single (one transpose)", "scaling": "strong", "sizes": sharded}
         if sweep is not None:
             line["ntt_sweep"] = sweep
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
@@ -399,6 +408,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 behind Python's back
+    # (NCCL prints its version there), so everything but the final line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args, rank)

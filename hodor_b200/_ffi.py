@@ -67,6 +67,8 @@ _SIGS = {
     "hodor_field_from_repr": (C.c_int, [C.c_int, u64p, u64p]),
     "hodor_field_into_repr": (C.c_int, [C.c_int, u64p, u64p]),
     "hodor_root_to_challenge": (C.c_int, [u8p, u64p, C.c_int]),
+    "hodor_hash_leaf": (C.c_int, [u64p, u8p]),
+    "hodor_hash_node": (C.c_int, [u8p, u8p, u8p]),
     "hodor_cuda_malloc": (vp, [C.c_size_t]),
     "hodor_cuda_free": (None, [vp]),
     "hodor_cuda_host_alloc": (vp, [C.c_size_t]),

@@ -254,6 +254,7 @@ void hodor_cuda_shutdown(void) {
     for (auto& kv : g_ctx->ntt_tables) {
         cudaFree(kv.second.pw.block);
         cudaFree(kv.second.tw_b_block);
+        cudaFree(kv.second.tw_direct_block);
     }
     if (g_ctx->ws) cudaFree(g_ctx->ws);
     for (int i = 0; i < 2; i++)
@@ -362,6 +363,25 @@ int hodor_root_to_challenge(const uint8_t root[32], uint64_t out[4], int field_i
     int rc = ops->h_root_to_challenge(root, r);
     if (rc) return fail(rc, "digest does not reduce into the field");
     fe_to_u64(r, out);
+    return HODOR_OK;
+}
+// O(log n) verifier-side hashing (IopTree::verify / get_path's leaf-pair hash): single hashes on the
+// host with the same compression code the kernels use, compiled for the host.
+int hodor_hash_leaf(const uint64_t leaf[4], uint8_t out[32]) {
+    static const B2sState key = b2s_keyed_state();
+    uint32_t w[8];
+    memcpy(w, leaf, 32);
+    const Digest d = hash_leaf32(key, w);
+    memcpy(out, d.w, 32);
+    return HODOR_OK;
+}
+int hodor_hash_node(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]) {
+    static const B2sState key = b2s_keyed_state();
+    Digest l, r;
+    memcpy(l.w, left, 32);
+    memcpy(r.w, right, 32);
+    const Digest d = hash_node64(key, l, r);
+    memcpy(out, d.w, 32);
     return HODOR_OK;
 }
 

@@ -43,6 +43,8 @@ struct NttTables {
     PowTables pw;            // powers of omega, exponents [0, 2^log_n)
     uint4* tw_b[10] = {};    // tw_b[B][x] = omega^(x << (log_n - B)), B in 6..9 (as used by the plan)
     uint4* tw_b_block = nullptr;
+    uint4* tw_direct[17] = {};  // tw_direct[k][x] = omega^(x << (log_n - k)), x < 2^k: flat inter-pass twiddles, k <= 16
+    uint4* tw_direct_block = nullptr;
     Fe wr[7];                // omega_16^k, k = 1..7
     size_t bytes = 0;
 };

@@ -160,6 +160,7 @@ struct Ops {
         for (auto& kv : c.ntt_tables) {
             cudaFree(kv.second.pw.block);
             cudaFree(kv.second.tw_b_block);
+            cudaFree(kv.second.tw_direct_block);
         }
         c.pow_tables.clear();
         c.ntt_tables.clear();
@@ -230,6 +231,38 @@ struct Ops {
                 }
                 HODOR_CUDA_TRY(cudaGetLastError());
                 HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                // flat inter-pass twiddle tables for every non-last pass whose sub-transform N = 2^(s+B)
+                // is at most 2^16 (for 2^24 = 8+8+8 that is pass 2: 65536 entries, 2 MiB)
+                size_t dtotal = 0;
+                uint32_t below = log_n;
+                for (int i = 0; i + 1 < plan.passes; i++) {
+                    const uint32_t k = below;  // s + B of pass i
+                    below -= plan.b[i];
+                    if (k <= 16 && t.tw_direct[k] == nullptr) {
+                        t.tw_direct[k] = (uint4*)1;  // mark
+                        dtotal += (size_t)1 << k;
+                    }
+                }
+                if (dtotal) {
+                    HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_direct_block, dtotal * sizeof(Fe)));
+                    uint4* dcur = t.tw_direct_block;
+                    for (uint32_t k = 0; k <= 16; k++) {
+                        if (t.tw_direct[k] == nullptr) continue;
+                        const Fe base = pow2k(omega, log_n - k);
+                        HODOR_CUDA_TRY(cudaMemcpyAsync(d_base, &base, sizeof(Fe), cudaMemcpyHostToDevice, st));
+                        HODOR_CUDA_TRY(cudaStreamSynchronize(st));  // `base` is a stack temporary
+                        t.tw_direct[k] = dcur;
+                        const uint32_t cnt = 1u << k;
+                        {
+                            ProfScope ps(c, st, "pow_table");
+                            pow_table_kernel<F><<<dim3((cnt + 255) / 256, 1), 256, 0, st>>>(dcur, d_base, nullptr, cnt, 0u);
+                        }
+                        HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                        dcur += 2 * (size_t)cnt;
+                    }
+                    HODOR_CUDA_TRY(cudaGetLastError());
+                    t.bytes += dtotal * sizeof(Fe);
+                }
                 cudaFree(d_base);
                 c.table_bytes += t.bytes;
             }
@@ -402,6 +435,7 @@ struct Ops {
             const bool last = (i == plan.passes - 1);
             p.s = below;
             p.tw_b = tw->tw_b[b];
+            p.tw_direct = (!last && below + b <= 16) ? tw->tw_direct[below + b] : nullptr;
             p.tw_shift = log_n - below - b;
             p.flags = last ? flags : 0;
             if (!last) {

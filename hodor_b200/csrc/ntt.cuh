@@ -48,6 +48,7 @@ struct NttPass {
     uint32_t coset_stride_lo, coset_stride_hi;  // elements between per-coset tables
     TwoLevel tw;        // powers of omega
     const uint4* tw_b;  // omega_B^x, x in [0, 2^B)
+    const uint4* tw_direct;  // inter-pass twiddles omega_N^x, x in [0, N = 2^(s+B)), when N <= 2^16; else null
     TwoLevel coset;     // pass 1 of a scaled transform: shift_i^j tables, coset i at +i*coset_stride
     TwoLevel out_pow;   // PASS_OUT_POW
     Fe out_const;       // PASS_OUT_CONST
@@ -248,8 +249,13 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
     auto store_global = [&](uint32_t pos, uint32_t c, Fe v) {
         const uint32_t kloc = local_out_index<B>(pos);
         if constexpr (!LAST) {
-            const uint64_t e = ((uint64_t)kloc * (col0 + c)) << p.tw_shift;
-            v = fld.mul(v, two_level_pow(fld, p.tw, 0, 0, e));
+            // omega_N^(kloc * r): one lookup when the sub-transform is short enough for a flat table
+            // (2 MiB at N = 2^16, L2 resident), else hi * lo from the two-level tables (one more multiply)
+            const uint64_t prod = (uint64_t)kloc * (col0 + c);
+            Fe w;
+            if (p.tw_direct != nullptr) w = ld_fe(p.tw_direct, (size_t)prod);
+            else w = two_level_pow(fld, p.tw, 0, 0, prod << p.tw_shift);
+            v = fld.mul(v, w);
             st_fe(p.out, out_base + ((size_t)kloc << p.s) + c, v);
         } else {
             const uint32_t i = (coset_hi << li) | (c & ((1u << li) - 1u));

@@ -70,6 +70,10 @@ int hodor_field_into_repr(int field_id, const uint64_t mont[4], uint64_t out[4])
 /* Blake2sLeafEncoder::interpret_hash / IopTree::encode_root_into_challenge
  * (src/iop/blake2s_trivial_iop.rs:48-60, :226-228) */
 int hodor_root_to_challenge(const uint8_t root[32], uint64_t out[4], int field_id);
+/* IopTreeHasher::hash_leaf / hash_node for single items (src/iop/blake2s_trivial_iop.rs:81-104):
+ * verifier-side O(log n) work (IopTree::verify, the leaf-pair hash of get_path) on the host. */
+int hodor_hash_leaf(const uint64_t leaf[4], uint8_t out[32]);
+int hodor_hash_node(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]);
 
 /* ---- memory helpers ---------------------------------------------------------------------- */
 void* hodor_cuda_malloc(size_t bytes);

@@ -1,0 +1,408 @@
+// hodor_b200.hpp -- C++17 host-side mirror of the reference interface for the hot path, on top of
+// the C ABI of hodor_b200.h.  Header only; link with -lhodor_b200.
+//
+// The reference (matter-labs/hodor @ 76fc894) is Rust and its toolchain is not available in this
+// environment, so the host side that a Rust caller would write is mirrored here in C++ with the
+// same names, argument meaning and error behaviour:
+//
+//   Domain<F>                         src/domains/mod.rs:14-70
+//   Polynomial<F, Coefficients|Values> src/polynomials/mod.rs:26-34, 343-352, 611-638, 773-815
+//   Blake2sIopTree<F>, TrivialBlake2sIOP<F>, TrivialBlake2sIopQuery<F>
+//                                     src/iop/mod.rs:49-92, src/iop/blake2s_trivial_iop.rs:107-368
+//   NaiveFriIop<F>, FRIProofPrototype<F>, FRIProof<F>
+//                                     src/fri/mod.rs:26-154, src/fri/fri_on_values.rs:11-159,
+//                                     src/fri/query_producer.rs:10-53
+//
+// `Result<_, SynthesisError>` becomes a thrown SynthesisError; the reference's assert!/expect panics
+// become std::logic_error.  `Worker` is accepted and ignored (the CUDA grid replaces the thread pool).
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "hodor_b200.h"
+
+namespace hodor_b200 {
+
+struct SynthesisError : std::runtime_error {  // src/lib.rs:40-46
+    explicit SynthesisError(const std::string& what) : std::runtime_error(what) {}
+};
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& what) : std::runtime_error(what) {}
+};
+
+inline int check(int rc) {
+    if (rc >= 0) return rc;
+    const std::string msg = hodor_cuda_last_error();
+    if (rc == HODOR_ERR_DOMAIN) throw SynthesisError("General error for now: " + msg);
+    if (rc == HODOR_ERR_INVALID_ARG) throw std::logic_error(msg);
+    throw CudaError(msg);
+}
+inline void init(int device = 0) { check(hodor_cuda_init(device)); }
+
+struct Worker {};  // src/fft/multicore.rs:17-103
+
+using Digest = std::array<uint8_t, 32>;
+
+// One field element: 4 little-endian u64 limbs, Montgomery form -- `Fr(FrRepr([u64; 4]))`.
+template <int FIELD_ID>
+struct Fr {
+    static constexpr int ID = FIELD_ID;
+    uint64_t l[4] = {0, 0, 0, 0};
+    bool operator==(const Fr& o) const { return std::memcmp(l, o.l, 32) == 0; }
+    bool operator!=(const Fr& o) const { return !(*this == o); }
+
+    static Fr zero() { return Fr{}; }
+    static Fr one() {
+        Fr r;
+        check(hodor_field_constants(ID, nullptr, r.l, nullptr, nullptr, nullptr, nullptr, nullptr));
+        return r;
+    }
+    static Fr multiplicative_generator() {
+        Fr r;
+        check(hodor_field_constants(ID, nullptr, nullptr, r.l, nullptr, nullptr, nullptr, nullptr));
+        return r;
+    }
+    static Fr root_of_unity() {
+        Fr r;
+        check(hodor_field_constants(ID, nullptr, nullptr, nullptr, r.l, nullptr, nullptr, nullptr));
+        return r;
+    }
+    static uint32_t S() {
+        uint32_t s = 0;
+        check(hodor_field_constants(ID, nullptr, nullptr, nullptr, nullptr, &s, nullptr, nullptr));
+        return s;
+    }
+    static Fr from_u64(uint64_t x) {  // PrimeField::from_str / from_repr
+        const uint64_t plain[4] = {x, 0, 0, 0};
+        Fr r;
+        check(hodor_field_from_repr(ID, plain, r.l));
+        return r;
+    }
+    void mul_assign(const Fr& o) { check(hodor_field_mul(ID, l, o.l, l)); }
+    void add_assign(const Fr& o) { check(hodor_field_add(ID, l, o.l, l)); }
+    void sub_assign(const Fr& o) { check(hodor_field_sub(ID, l, o.l, l)); }
+    void square() { mul_assign(*this); }
+    void double_() { add_assign(*this); }
+    Fr pow(uint64_t e) const {
+        Fr r;
+        check(hodor_field_pow(ID, l, e, r.l));
+        return r;
+    }
+    // Field::inverse returns Option<Self>: empty on zero
+    std::pair<bool, Fr> inverse() const {
+        Fr r;
+        if (hodor_field_inverse(ID, l, r.l) != HODOR_OK) return {false, Fr{}};
+        return {true, r};
+    }
+};
+using Bn256RsFr = Fr<HODOR_FIELD_BLS12_381_FR>;  // the field src/bn256.rs declares
+using Bn254Fr = Fr<HODOR_FIELD_BN254_FR>;
+using Stark252Fr = Fr<HODOR_FIELD_STARK252>;
+
+template <class F>
+struct Domain {
+    uint64_t size = 0;
+    uint64_t power_of_two = 0;
+    F generator;
+
+    static Domain new_for_size(uint64_t size) {  // :21-44
+        uint64_t s = 1, k = 0;
+        while (s < size) {
+            s <<= 1;
+            k++;
+        }
+        Domain d;
+        d.size = s;
+        d.power_of_two = k;
+        check(hodor_domain_generator(F::ID, (uint32_t)k, d.generator.l));  // Err(SynthesisError::Error)
+        return d;
+    }
+    static std::vector<size_t> coset_for_natural_index_and_size(size_t natural_index, size_t domain_size) {
+        if (domain_size <= 1 || (domain_size & (domain_size - 1))) throw std::logic_error("assert!(domain_size.is_power_of_two())");
+        std::vector<size_t> c{natural_index, (natural_index + domain_size / 2) % domain_size};
+        std::sort(c.begin(), c.end());
+        return c;
+    }
+    static std::pair<size_t, size_t> index_and_size_for_next_domain(size_t natural_index, size_t domain_size) {
+        if (domain_size <= 1 || (domain_size & (domain_size - 1))) throw std::logic_error("assert!(domain_size.is_power_of_two())");
+        const size_t next = domain_size / 2;
+        return {natural_index < next ? natural_index : natural_index - next, next};
+    }
+};
+
+struct Coefficients {};
+struct Values {};
+
+template <class F, class Form>
+class Polynomial {
+  public:
+    uint32_t exp = 0;
+    F omega, omegainv, geninv, minv;
+
+    static Polynomial from_coeffs(std::vector<F> v) {
+        static_assert(std::is_same<Form, Coefficients>::value, "from_coeffs makes Polynomial<F, Coefficients>");
+        return Polynomial(std::move(v));
+    }
+    static Polynomial from_values(std::vector<F> v) {
+        static_assert(std::is_same<Form, Values>::value, "from_values makes Polynomial<F, Values>");
+        return Polynomial(std::move(v));
+    }
+    size_t size() const { return coeffs_.size(); }
+    const std::vector<F>& as_ref() const { return coeffs_; }
+    std::vector<F>& as_mut() { return coeffs_; }
+    std::vector<F> into_coeffs() && { return std::move(coeffs_); }
+    bool operator==(const Polynomial& o) const { return coeffs_ == o.coeffs_; }
+
+    void distribute_powers(const Worker&, const F& g) {  // src/fft/mod.rs:110-123
+        check(hodor_cuda_distribute_powers(raw(), coeffs_.size(), g.l, F::ID));
+    }
+    // ---- Polynomial<F, Coefficients> -----------------------------------------------------------
+    Polynomial<F, Values> fft(const Worker&) && {  // :611-624
+        require<Coefficients>();
+        check(hodor_cuda_fft(raw(), exp, 0, F::ID));
+        return Polynomial<F, Values>::adopt(std::move(coeffs_));
+    }
+    Polynomial<F, Values> coset_fft(const Worker&) && {  // :626-631
+        require<Coefficients>();
+        check(hodor_cuda_fft(raw(), exp, 1, F::ID));
+        return Polynomial<F, Values>::adopt(std::move(coeffs_));
+    }
+    Polynomial<F, Values> lde(const Worker&, size_t factor) && { return do_lde(factor, 0); }        // :343-346
+    Polynomial<F, Values> coset_lde(const Worker&, size_t factor) && { return do_lde(factor, 1); }  // :348-352
+    // ---- Polynomial<F, Values> -----------------------------------------------------------------
+    Polynomial<F, Coefficients> ifft(const Worker&) && {  // :773-798
+        require<Values>();
+        check(hodor_cuda_ifft(raw(), exp, 0, F::ID));
+        return Polynomial<F, Coefficients>::adopt(std::move(coeffs_));
+    }
+    Polynomial<F, Coefficients> icoset_fft(const Worker&) && {  // :800-807
+        require<Values>();
+        check(hodor_cuda_ifft(raw(), exp, 1, F::ID));
+        return Polynomial<F, Coefficients>::adopt(std::move(coeffs_));
+    }
+    Polynomial clone() const { return Polynomial(coeffs_); }
+
+    static Polynomial adopt(std::vector<F> v) { return Polynomial(std::move(v)); }
+
+  private:
+    std::vector<F> coeffs_;
+
+    explicit Polynomial(std::vector<F> v) : coeffs_(std::move(v)) {  // from_values / from_coeffs, :713-742
+        const auto dom = Domain<F>::new_for_size(std::max<size_t>(1, coeffs_.size()));
+        coeffs_.resize(dom.size, F::zero());
+        exp = (uint32_t)dom.power_of_two;
+        omega = dom.generator;
+        omegainv = omega.inverse().second;
+        geninv = F::multiplicative_generator().inverse().second;
+        minv = F::from_u64(dom.size).inverse().second;
+    }
+    uint64_t* raw() { return reinterpret_cast<uint64_t*>(coeffs_.data()); }
+    template <class Need>
+    void require() const {
+        static_assert(std::is_same<Form, Need>::value, "wrong polynomial form for this transform");
+    }
+    Polynomial<F, Values> do_lde(size_t factor, int coset) {
+        require<Coefficients>();
+        if (factor == 0 || (factor & (factor - 1))) throw std::logic_error("assert!(factor.is_power_of_two())");
+        uint32_t log_f = 0;
+        while (((size_t)1 << log_f) < factor) log_f++;
+        (void)Domain<F>::new_for_size(coeffs_.size() * factor);  // same Err as src/polynomials/mod.rs:435
+        std::vector<F> out(coeffs_.size() * factor);
+        check(hodor_cuda_lde(raw(), exp, log_f, coset, reinterpret_cast<uint64_t*>(out.data()), F::ID));
+        return Polynomial<F, Values>::adopt(std::move(out));
+    }
+};
+
+// ---- IOP -------------------------------------------------------------------------------------
+template <class F>
+struct Blake2sTreeHasher {  // src/iop/blake2s_trivial_iop.rs:63-105
+    static Digest hash_leaf(const F& v) {
+        Digest d;
+        check(hodor_hash_leaf(v.l, d.data()));
+        return d;
+    }
+    static Digest hash_node(const Digest& l, const Digest& r) {
+        Digest d;
+        check(hodor_hash_node(l.data(), r.data(), d.data()));
+        return d;
+    }
+};
+
+template <class F>
+struct TrivialBlake2sIopQuery {  // :343-368
+    size_t index = 0;
+    F value_;
+    std::vector<Digest> path_;
+    size_t natural_index() const { return index; }
+    size_t tree_index() const { return index; }
+    const F& value() const { return value_; }
+    const std::vector<Digest>& path() const { return path_; }
+};
+
+template <class F>
+class Blake2sIopTree {  // :107-280
+  public:
+    static Blake2sIopTree create(const std::vector<F>& leafs) {
+        const size_t n = leafs.size();
+        if (n < 2 || (n & (n - 1))) throw std::logic_error("assert!(num_leafs == num_leafs.next_power_of_two())");
+        Blake2sIopTree t;
+        t.nodes_.resize(n);
+        check(hodor_cuda_merkle_build(reinterpret_cast<const uint64_t*>(leafs.data()), n,
+                                      reinterpret_cast<uint8_t*>(t.nodes_.data()), F::ID));
+        return t;
+    }
+    uint64_t size() const { return nodes_.size(); }
+    Digest get_root() const { return nodes_[1]; }
+    static F encode_root_into_challenge(const Digest& root) {
+        F c;
+        check(hodor_root_to_challenge(root.data(), c.l, F::ID));
+        return c;
+    }
+    F get_challenge_scalar_from_root() const { return encode_root_into_challenge(get_root()); }
+    static bool verify(const Digest& root, const F& leaf_value, const std::vector<Digest>& path, size_t tree_index) {
+        Digest h = Blake2sTreeHasher<F>::hash_leaf(leaf_value);
+        size_t idx = tree_index;
+        for (const Digest& el : path) {
+            h = (idx & 1) == 0 ? Blake2sTreeHasher<F>::hash_node(h, el) : Blake2sTreeHasher<F>::hash_node(el, h);
+            idx >>= 1;
+        }
+        return h == root;
+    }
+    std::vector<Digest> get_path(size_t tree_index, const std::vector<F>& leafs_values) const {
+        std::vector<Digest> path{Blake2sTreeHasher<F>::hash_leaf(leafs_values[tree_index ^ 1])};
+        for (size_t idx = (nodes_.size() + tree_index) >> 1; idx > 1; idx >>= 1) path.push_back(nodes_[idx ^ 1]);
+        return path;
+    }
+    const std::vector<Digest>& nodes() const { return nodes_; }
+
+  private:
+    std::vector<Digest> nodes_;
+};
+
+template <class F>
+class TrivialBlake2sIOP {  // :282-341
+  public:
+    using Query = TrivialBlake2sIopQuery<F>;
+    static TrivialBlake2sIOP create(const std::vector<F>& leafs) { return TrivialBlake2sIOP{Blake2sIopTree<F>::create(leafs)}; }
+    Digest get_root() const { return tree.get_root(); }
+    F get_challenge_scalar_from_root() const { return tree.get_challenge_scalar_from_root(); }
+    static bool verify_query(const Query& q, const Digest& root) {
+        return Blake2sIopTree<F>::verify(root, q.value(), q.path(), q.tree_index());
+    }
+    Query query(size_t natural_index, const std::vector<F>& leafs) const {
+        if (natural_index >= tree.size() || natural_index >= leafs.size()) throw std::logic_error("assert!(natural_index < size)");
+        return Query{natural_index, leafs[natural_index], tree.get_path(natural_index, leafs)};
+    }
+    bool operator==(const TrivialBlake2sIOP& o) const { return get_root() == o.get_root(); }
+    Blake2sIopTree<F> tree;
+};
+
+// ---- FRI -------------------------------------------------------------------------------------
+template <class F>
+struct FRIProof {  // src/fri/mod.rs:140-154
+    std::vector<TrivialBlake2sIopQuery<F>> queries;
+    std::vector<Digest> roots;
+    std::vector<F> final_coefficients;
+    size_t initial_degree_plus_one = 0, output_coeffs_at_degree_plus_one = 0, lde_factor = 0;
+    const std::vector<F>& get_final_coefficients() const { return final_coefficients; }
+};
+
+template <class F>
+class FRIProofPrototype {  // src/fri/mod.rs:107-138; trees and layer values stay in HBM behind the handle
+  public:
+    std::vector<F> challenges;
+    Digest final_root{};
+    std::vector<F> final_coefficients;
+    size_t initial_degree_plus_one = 0, output_coeffs_at_degree_plus_one = 0, lde_factor = 0;
+
+    FRIProofPrototype(hodor_fri_proto* h, size_t n, size_t factor, size_t out) : handle_(h, &hodor_cuda_fri_free), n_(n) {
+        lde_factor = factor;
+        output_coeffs_at_degree_plus_one = out;
+        initial_degree_plus_one = n / factor;
+        steps_ = check(hodor_cuda_fri_num_steps(h));
+        roots_.resize(steps_ + 1);
+        challenges.resize(steps_);
+        final_coefficients.resize(out);
+        check(hodor_cuda_fri_summary(h, reinterpret_cast<uint8_t*>(roots_.data()), reinterpret_cast<uint64_t*>(challenges.data()),
+                                     reinterpret_cast<uint64_t*>(final_coefficients.data())));
+        final_root = roots_.back();
+    }
+    int num_steps() const { return steps_; }
+    std::vector<Digest> get_roots() const { return roots_; }
+    Digest get_final_root() const { return final_root; }
+    std::vector<F> get_final_coefficients() const { return final_coefficients; }
+    std::vector<F> intermediate_values(size_t i) const {  // intermediate_values[i] as a host vector
+        std::vector<F> v(n_ >> (i + 1));
+        check(hodor_cuda_fri_layer(handle_.get(), (uint32_t)i + 1, nullptr, reinterpret_cast<uint64_t*>(v.data())));
+        return v;
+    }
+    std::vector<Digest> commitment_nodes(size_t layer) const {  // layer 0 = l0_commitment
+        std::vector<Digest> v(n_ >> layer);
+        check(hodor_cuda_fri_layer(handle_.get(), (uint32_t)layer, reinterpret_cast<uint8_t*>(v.data()), nullptr));
+        return v;
+    }
+    TrivialBlake2sIopQuery<F> query(size_t layer, size_t natural_index) const {
+        const size_t size = n_ >> layer;
+        size_t len = 0;
+        while (((size_t)1 << len) < size) len++;
+        TrivialBlake2sIopQuery<F> q;
+        q.index = natural_index;
+        q.path_.resize(len);
+        check(hodor_cuda_fri_query(handle_.get(), (uint32_t)layer, natural_index, q.value_.l,
+                                   reinterpret_cast<uint8_t*>(q.path_.data())));
+        return q;
+    }
+    FRIProof<F> produce_proof(size_t natural_first_element_index) const {  // src/fri/query_producer.rs:10-53
+        FRIProof<F> proof;
+        size_t domain_size = initial_degree_plus_one * lde_factor, domain_idx = natural_first_element_index;
+        for (int layer = 0; layer <= steps_; layer++) {
+            for (size_t idx : Domain<F>::coset_for_natural_index_and_size(domain_idx, domain_size))
+                proof.queries.push_back(query(layer, idx));
+            proof.roots.push_back(roots_[layer]);
+            std::tie(domain_idx, domain_size) = Domain<F>::index_and_size_for_next_domain(domain_idx, domain_size);
+        }
+        proof.final_coefficients = final_coefficients;
+        proof.initial_degree_plus_one = initial_degree_plus_one;
+        proof.output_coeffs_at_degree_plus_one = output_coeffs_at_degree_plus_one;
+        proof.lde_factor = lde_factor;
+        return proof;
+    }
+
+  private:
+    std::unique_ptr<hodor_fri_proto, void (*)(hodor_fri_proto*)> handle_;
+    size_t n_;
+    int steps_ = 0;
+    std::vector<Digest> roots_;
+};
+
+template <class F>
+struct NaiveFriIop {  // src/fri/mod.rs:63-105
+    static constexpr size_t DEGREE = 2;
+    static FRIProofPrototype<F> proof_from_lde(const Polynomial<F, Values>& lde_values, size_t lde_factor,
+                                               size_t output_coeffs_at_degree_plus_one, const Worker&) {
+        hodor_fri_proto* h = hodor_cuda_fri_commit(reinterpret_cast<const uint64_t*>(lde_values.as_ref().data()),
+                                                   lde_values.size(), (uint32_t)lde_factor,
+                                                   (uint32_t)output_coeffs_at_degree_plus_one, 0, F::ID);
+        if (!h) {
+            const std::string msg = hodor_cuda_last_error();
+            if (msg.find("2-adicity") != std::string::npos) throw SynthesisError(msg);
+            if (msg.find("fri_commit:") != std::string::npos) throw std::logic_error(msg);
+            throw CudaError(msg);
+        }
+        return FRIProofPrototype<F>(h, lde_values.size(), lde_factor, output_coeffs_at_degree_plus_one);
+    }
+    static FRIProof<F> prototype_into_proof(const FRIProofPrototype<F>& prototype, const Polynomial<F, Values>&,
+                                            size_t natural_first_element_index) {
+        return prototype.produce_proof(natural_first_element_index);
+    }
+};
+
+}  // namespace hodor_b200

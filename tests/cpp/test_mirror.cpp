@@ -1,0 +1,203 @@
+// C++ parity tests through the host mirror (include/hodor_b200.hpp), shaped after the reference's own
+// tests.  Links the product (libhodor_b200.so) and, as the checker only, the
+// CPU oracle (oracle/_build/libhodor_oracle.so).  Needs a B200; run by tests/test_cpp_mirror.py.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "hodor_b200.hpp"
+
+using namespace hodor_b200;
+
+extern "C" {  // oracle/hodor_oracle.c (TEST ONLY)
+int oracle_random_elements(int field, uint64_t* out, size_t count, uint64_t seed);
+int oracle_serial_fft(int field, uint64_t* a, const uint64_t* omega, uint32_t log_n);
+int oracle_lde(int field, const uint64_t* coeffs, uint32_t log_n, uint32_t factor, int coset, uint64_t* out, uint32_t cpus);
+int oracle_merkle_create(int field, const uint64_t* leaves, size_t n, uint8_t* nodes, uint32_t cpus);
+}
+
+static int failures = 0;
+#define CHECK(cond)                                                          \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);      \
+            failures++;                                                      \
+        }                                                                    \
+    } while (0)
+
+template <class F>
+static std::vector<F> random_vec(size_t n, uint64_t seed) {
+    std::vector<F> v(n);
+    oracle_random_elements(F::ID, reinterpret_cast<uint64_t*>(v.data()), n, seed);
+    return v;
+}
+
+// test_worker_size (src/fft/mod.rs:281): forward == serial_fft, inverse round trip == input
+template <class F>
+static void test_fft_roundtrip() {
+    const Worker worker;
+    for (uint32_t log_n : {0u, 1u, 5u, 10u, 13u, 16u}) {
+        const auto a = random_vec<F>((size_t)1 << log_n, 100 + log_n);
+        auto coeffs = Polynomial<F, Coefficients>::from_coeffs(a);
+        const F omega = coeffs.omega;
+        auto values = std::move(coeffs).fft(worker);
+        std::vector<F> want = a;
+        oracle_serial_fft(F::ID, reinterpret_cast<uint64_t*>(want.data()), omega.l, log_n);
+        CHECK(values.as_ref() == want);
+        auto back = std::move(values).ifft(worker);
+        CHECK(back.as_ref() == a);
+        auto cback = Polynomial<F, Coefficients>::from_coeffs(a).coset_fft(worker).icoset_fft(worker);
+        CHECK(cback.as_ref() == a);
+    }
+}
+
+// test_lde_correctness / test_coset_lde_correctness (src/polynomials/mod.rs:988, 1036)
+template <class F>
+static void test_lde_correctness() {
+    const Worker worker;
+    for (auto [log_n, factor] : {std::pair<uint32_t, size_t>{2, 16}, {8, 8}, {12, 8}, {14, 2}}) {
+        const size_t n = (size_t)1 << log_n;
+        const auto a = random_vec<F>(n, 7 * log_n + factor);
+        for (int coset = 0; coset < 2; coset++) {
+            auto poly = Polynomial<F, Coefficients>::from_coeffs(a);
+            auto lde = coset ? std::move(poly).coset_lde(worker, factor) : std::move(poly).lde(worker, factor);
+            std::vector<F> want(n * factor);
+            oracle_lde(F::ID, reinterpret_cast<const uint64_t*>(a.data()), log_n, (uint32_t)factor, coset,
+                       reinterpret_cast<uint64_t*>(want.data()), (uint32_t)factor);
+            CHECK(lde.as_ref() == want);
+            // multi-coset LDE == (coset) NTT of the zero-padded vector
+            std::vector<F> padded(n * factor);
+            std::copy(a.begin(), a.end(), padded.begin());
+            auto p2 = Polynomial<F, Coefficients>::from_coeffs(padded);
+            auto full = coset ? std::move(p2).coset_fft(worker) : std::move(p2).fft(worker);
+            CHECK(full.as_ref() == lde.as_ref());
+        }
+    }
+    bool threw = false;
+    try {
+        auto p = Polynomial<F, Coefficients>::from_coeffs(random_vec<F>(4, 1));
+        (void)std::move(p).lde(worker, 3);
+    } catch (const std::logic_error&) {
+        threw = true;
+    }
+    CHECK(threw);  // assert!(factor.is_power_of_two())
+}
+
+// make_small_iop (src/iop/blake2s_trivial_iop.rs:390-408) + bit-exact nodes
+template <class F>
+static void test_small_iop() {
+    std::vector<F> inputs;
+    F f = F::one();
+    for (int i = 0; i < 64; i++) {
+        inputs.push_back(f);
+        f.double_();
+    }
+    const auto iop = TrivialBlake2sIOP<F>::create(inputs);
+    const Digest root = iop.get_root();
+    for (size_t i = 0; i < 64; i++) {
+        const auto q = iop.query(i, inputs);
+        CHECK(TrivialBlake2sIOP<F>::verify_query(q, root));
+        auto bad = q;
+        bad.value_.double_();
+        CHECK(!TrivialBlake2sIOP<F>::verify_query(bad, root));
+    }
+    const auto leaves = random_vec<F>(1 << 13, 5);
+    const auto tree = Blake2sIopTree<F>::create(leaves);
+    std::vector<Digest> want(leaves.size());
+    oracle_merkle_create(F::ID, reinterpret_cast<const uint64_t*>(leaves.data()), leaves.size(),
+                         reinterpret_cast<uint8_t*>(want.data()), 4);
+    CHECK(tree.nodes() == want);
+}
+
+// test_one_fri_step (src/fri/mod.rs:252-331) and the query producer
+template <class F>
+static void test_one_fri_step() {
+    const Worker worker;
+    std::vector<F> lde_coeffs;
+    F f = F::one();
+    for (int i = 0; i < 4; i++) {
+        lde_coeffs.push_back(f);
+        f.double_();
+    }
+    const size_t lde_factor = 4;
+    auto lde_values = Polynomial<F, Coefficients>::from_coeffs(lde_coeffs).lde(worker, lde_factor);
+    const auto proto = NaiveFriIop<F>::proof_from_lde(lde_values, lde_factor, 2, worker);
+    CHECK(proto.num_steps() == 1);
+    const F challenge = proto.challenges[0];
+    std::vector<F> new_coeffs;
+    for (size_t k = 0; k < 4; k += 2) {
+        F tmp = lde_coeffs[k + 1];
+        tmp.mul_assign(challenge);
+        tmp.add_assign(lde_coeffs[k]);
+        new_coeffs.push_back(tmp);
+    }
+    CHECK(proto.final_coefficients == new_coeffs);
+    auto next_lde = Polynomial<F, Coefficients>::from_coeffs(new_coeffs).lde(worker, lde_factor);
+    CHECK(proto.intermediate_values(0) == next_lde.as_ref());
+    CHECK(proto.get_roots()[1] == TrivialBlake2sIOP<F>::create(next_lde.as_ref()).get_root());
+    // hand interpolation at coset index 3 (:283-300)
+    const size_t idx = 3, pair = idx + lde_factor * 2;
+    const F divisor = lde_values.omegainv.pow(idx);
+    const F two_inv = F::from_u64(2).inverse().second;
+    F t0 = lde_values.as_ref()[idx];
+    t0.add_assign(lde_values.as_ref()[pair]);
+    F t1 = lde_values.as_ref()[idx];
+    t1.sub_assign(lde_values.as_ref()[pair]);
+    t1.mul_assign(divisor);
+    t1.mul_assign(challenge);
+    t0.add_assign(t1);
+    t0.mul_assign(two_inv);
+    CHECK(next_lde.as_ref()[idx] == t0);
+    for (size_t start : {1u, 3u, 7u, 12u}) {
+        const auto proof = NaiveFriIop<F>::prototype_into_proof(proto, lde_values, start);
+        CHECK(proof.queries.size() == 2 * proof.roots.size());
+        for (size_t k = 0; k < proof.queries.size(); k++)
+            CHECK(TrivialBlake2sIOP<F>::verify_query(proof.queries[k], proof.roots[k / 2]));
+    }
+    bool threw = false;
+    try {
+        (void)NaiveFriIop<F>::proof_from_lde(lde_values, 16, 1, worker);  // zero folding steps
+    } catch (const std::logic_error&) {
+        threw = true;
+    }
+    CHECK(threw);
+}
+
+template <class F>
+static void test_domain() {
+    CHECK(Domain<F>::new_for_size(5).size == 8);
+    bool threw = false;
+    try {
+        (void)Domain<F>::new_for_size(((uint64_t)1 << F::S()) + 1);
+    } catch (const SynthesisError&) {
+        threw = true;
+    }
+    CHECK(threw || F::S() >= 63);
+    F g = Domain<F>::new_for_size(16).generator;
+    CHECK(g.pow(16) == F::one() && g.pow(8) != F::one());
+}
+
+template <class F>
+static void run_all(const char* name) {
+    const int before = failures;
+    test_domain<F>();
+    test_fft_roundtrip<F>();
+    test_lde_correctness<F>();
+    test_small_iop<F>();
+    test_one_fri_step<F>();
+    std::printf("%s: %s\n", name, failures == before ? "ok" : "FAILED");
+}
+
+int main() {
+    try {
+        init(0);
+        run_all<Bn256RsFr>("bn256.rs Fr (BLS12-381 Fr)");
+        run_all<Bn254Fr>("BN254 Fr");
+        run_all<Stark252Fr>("Stark252");
+    } catch (const std::exception& e) {
+        std::printf("EXCEPTION: %s\n", e.what());
+        return 2;
+    }
+    std::printf("%d failure(s)\n", failures);
+    return failures ? 1 : 0;
+}
