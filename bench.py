@@ -263,9 +263,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     dom_ms = dom["total_ms"] / dom["count"]
     dom_bytes = alg_bytes.get(dom["name"], 64 * n * L)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (profiles/)
+    traffic, pipes = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom["name"]]
+        traffic = cap["traffic"]
+        pipes = {"fma_pipe_cycles_active_pct": cap["fma_pipe_cycles_active_pct"], "alu_pipe_inst_pct": cap["alu_pipe_inst_pct"],
+                 "source": "profiles/r01_traffic.json (ncu)"}
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-        "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak_gbs, "traffic": traffic, "int_pipes": pipes, "peak_source": peak_src,
         "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms, "share_of_step": dom["total_ms"] / kern_total,
         "kernels": {k: {"launches": r["count"], "ms_per_launch": r["total_ms"] / r["count"],
                         "share": r["total_ms"] / kern_total} for k, r in prof.items()},

@@ -475,7 +475,39 @@ int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domai
     if (!is_pow2(n) || n < 2 || !is_pow2(initial_domain_size) || (initial_domain_size >> layer) != n)
         return fail(HODOR_ERR_INVALID_ARG, "fri_fold: n must equal initial_domain_size >> layer, both powers of two");
     return ops->fri_fold(*c, (const uint4*)d_in, n, log2u(initial_domain_size), layer, (const uint4*)d_challenge,
-                         (uint4*)d_out, pick_stream(c, stream));
+                         (uint4*)d_out, 0, 1, pick_stream(c, stream));
+}
+int hodor_cuda_fri_fold_shard_dev(const void* d_in, uint64_t n_local, uint64_t initial_domain_size, uint32_t layer,
+                                  uint32_t log_g, uint32_t rank, const void* d_challenge, void* d_out, int field_id,
+                                  void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    const uint64_t g = (uint64_t)1 << log_g;
+    if (!is_pow2(n_local) || n_local < 2 || !is_pow2(initial_domain_size) || rank >= g ||
+        ((initial_domain_size >> layer) >> log_g) != n_local)
+        return fail(HODOR_ERR_INVALID_ARG, "fri_fold_shard: n_local must equal (initial_domain_size >> layer) / G, >= 2");
+    return ops->fri_fold(*c, (const uint4*)d_in, n_local, log2u(initial_domain_size), layer, (const uint4*)d_challenge,
+                         (uint4*)d_out, rank, g, pick_stream(c, stream));
+}
+int hodor_cuda_lde_cosets_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint32_t first_coset,
+                              uint32_t coset_stride, uint32_t log_count, void* d_out, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    const uint64_t L = (uint64_t)1 << log_factor, cnt = (uint64_t)1 << log_count;
+    if (log_count > log_factor || coset_stride == 0 || first_coset + (cnt - 1) * coset_stride >= L)
+        return fail(HODOR_ERR_INVALID_ARG, "lde_cosets: coset subset out of range");
+    if (d_coeffs == d_out) return fail(HODOR_ERR_INVALID_ARG, "lde_cosets: input and output must not alias");
+    Fe omega, coset_omega, mod, one, gen, root, shift0, step;
+    int rc = ops->h_domain_generator(log_n + log_factor, coset_omega);
+    if (rc) return fail(rc, "LDE domain larger than the field's 2-adicity");
+    ops->h_domain_generator(log_n, omega);
+    uint32_t s, nb;
+    ops->h_constants(mod, one, gen, root, s, nb);
+    ops->h_pow(coset_omega, first_coset, shift0);  // shift_i = [g] * w_{nL}^i, i = first + stride * t
+    if (coset) ops->h_mul(shift0, gen, shift0);
+    ops->h_pow(coset_omega, coset_stride, step);
+    return ops->ntt(*c, (const uint4*)d_coeffs, (uint4*)d_out, log_n, log_count, omega, &shift0, &step, 0, nullptr,
+                    pick_stream(c, stream));
 }
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
                                void* stream) {
@@ -749,7 +781,7 @@ hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t
     const uint32_t log_n0 = log2u(n);
     for (int i = 0; i < steps && !rc; i++) {
         const size_t m = n >> i;
-        rc = ops->fri_fold(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], st);
+        rc = ops->fri_fold(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], 0, 1, st);
         if (rc) break;
         rc = do_merkle(*c, ops, p->values[i + 1], m / 2, p->nodes[i + 1], p->roots + 2 * (i + 1), p->chal + 2 * (i + 1), st);
     }

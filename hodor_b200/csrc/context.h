@@ -142,7 +142,7 @@ struct FieldOps {
     int (*merkle_tail)(Ctx&, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
                        cudaStream_t st);
     int (*fri_fold)(Ctx&, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
-                    cudaStream_t st);
+                    uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st);
     int (*shard_rows)(Ctx&, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_g, uint32_t rank, const Fe& omega,
                       cudaStream_t st);
 };

@@ -441,7 +441,7 @@ struct Ops {
             if (!last) {
                 p.in = (i == 0) ? in : work;
                 p.out = work;
-                dim3 grid((unsigned)(n >> (b + 3)), L);
+                dim3 grid((unsigned)(((size_t)L << log_n) >> (b + 3)), 1);  // tile-major, coset fastest
                 if (i == 0 && coset) rc = launch_pass_b<true, false>(c, b, p, grid, st);
                 else rc = launch_pass_b<false, false>(c, b, p, grid, st);
             } else {
@@ -500,7 +500,7 @@ struct Ops {
     }
 
     static int fri_fold(Ctx& c, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
-                        cudaStream_t st) {
+                        uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st) {
         // omega_N^-1 of the INITIAL domain (src/fri/fri_on_values.rs:24-25), table over exponents < N/2
         maybe_evict(c);
         static std::map<uint32_t, Fe> inv_cache;  // guarded by Ctx::mu; a host inversion is ~400 host multiplies
@@ -522,7 +522,8 @@ struct Ops {
         const unsigned grid = (unsigned)((half + 255) / 256 > 148 * 16 ? 148 * 16 : (half + 255) / 256);
         {
             ProfScope ps(c, st, "fri_fold");
-            fri_fold_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), layer, chal, 0u);
+            fri_fold_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), layer, chal, idx_offset,
+                                                                idx_stride, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;

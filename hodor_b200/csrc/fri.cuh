@@ -16,15 +16,20 @@
 namespace hodor {
 
 template <class F>
+// `in` holds the slice v[idx_offset + idx_stride * t] of the layer (offset 0, stride 1: the whole
+// layer; offset r, stride G: rank r's cyclic slice of a layer sharded over G GPUs, whose fold pairs
+// (t, t + half) are then both local).
 __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* out, size_t half, TwoLevel winv,
-                                                       uint32_t layer, const uint4* challenge, uint32_t zero) {
+                                                       uint32_t layer, const uint4* challenge, uint64_t idx_offset,
+                                                       uint64_t idx_stride, uint32_t zero) {
     const Field<F> fld(threadIdx.x & zero);
     const Fe c = ld_fe(challenge, 0);
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < half; idx += (size_t)gridDim.x * blockDim.x) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t idx = t;
         const Fe f0 = ld_fe(in, idx), f1 = ld_fe(in, idx + half);
         const Fe even = fld.add(f0, f1);
         Fe odd = fld.sub(f0, f1);
-        odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, (uint64_t)idx << layer));
+        odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, (idx_offset + idx_stride * (uint64_t)t) << layer));
         odd = fld.mul(odd, c);
         st_fe(out, idx, fld.halve(fld.add(odd, even)));
     }

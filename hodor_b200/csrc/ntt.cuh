@@ -207,10 +207,14 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
     uint32_t col0 = 0;            // !LAST: first column of the tile
     const uint32_t li = p.log_l < 3 ? p.log_l : 3;  // coset bits inside c (LAST)
     if constexpr (!LAST) {
+        // The coset is the fastest-varying part of the block index: the L cosets of one tile are
+        // resident together, so pass 1 of an LDE fetches the shared coefficient tile from HBM once
+        // and the other L-1 readers hit L2 (ncu before this change: 4.3 GB read for 0.54 GB of input).
         const uint32_t s = p.s;
         const uint32_t col_groups = 1u << (s - 3);
-        const uint32_t u = blockIdx.x >> (s - 3), cg = blockIdx.x & (col_groups - 1u);
-        coset_hi = blockIdx.y;
+        const uint32_t tile = blockIdx.x >> p.log_l;
+        const uint32_t u = tile >> (s - 3), cg = tile & (col_groups - 1u);
+        coset_hi = blockIdx.x & ((1u << p.log_l) - 1u);
         col0 = cg * 8;
         in_base = ((size_t)u << (s + B)) + col0;
         out_base = (size_t)coset_hi * n + in_base;

@@ -1,0 +1,215 @@
+"""Coset LDE + FRI commit chain sharded over the G = 2^g GPUs of one box (BASELINE.json north star:
+"2^24 -> 2^28 coset LDE plus full FRI commit chain on 8 x B200").  One process per GPU,
+torch.distributed for the plumbing, hand-written CUDA through the C ABI for every compute step.
+
+Distribution:
+
+* LDE.  Cosets are independent (src/polynomials/mod.rs:572-587): rank r computes the cosets
+  i = r, r+G, ... of the L-coset LDE from the (replicated) coefficient vector with no communication.
+  Because out[i + L*k] and G | L, what rank r holds is exactly its CYCLIC slice v[r + G*tau] of the
+  natural-order LDE.
+* FRI fold.  The pairs (idx, idx + M/2) of src/fri/fri_on_values.rs:74-101 have equal residues mod G,
+  so on cyclic slices every fold is local (hodor_cuda_fri_fold_shard_dev), layer after layer.
+* Merkle trees want adjacent leaves together, i.e. natural-order BLOCKS.  The only exchange of the whole
+  pipeline is therefore, per committed layer, one all-to-all that turns cyclic slices into blocks
+  (each rank sends (G-1)/G of its slice once).  Rank q then builds the subtree over its block -- its
+  local root is node G + q of the reference's heap layout -- the G sub-roots are all-gathered (32 B
+  each) and every rank finishes the top log2(G) levels and the root -> challenge map redundantly.
+* When a layer has shrunk below `gather_below` values the rest of the chain is tiny and strictly
+  serial (root -> challenge -> fold), so the layer is all-gathered and finished on every rank with the
+  single-GPU chain (hodor_cuda_fri_commit); its first tree is that layer's commitment.
+
+The result is bit-identical to the single-GPU / reference chain: roots, challenges, final
+coefficients (tests/test_sharded_cpu.py on gloo with the oracle as compute double;
+tests/test_gpu_parity.py::test_sharded_lde_fri_single_gpu emulates all ranks on one GPU).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Protocol
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class FriShardBackend(Protocol):
+    def lde_cosets(self, coeffs, log_n, log_factor, coset, first, stride, log_count, field_id) -> torch.Tensor: ...
+
+    def merkle_build(self, leaves, field_id) -> torch.Tensor: ...  # (n, 4) int64 nodes, heap order
+
+    def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id) -> torch.Tensor: ...
+
+    def fri_commit(self, values, lde_factor, out_coeffs, field_id): ...  # -> (roots, challenges, final_coeffs)
+
+    def hash_node(self, left: bytes, right: bytes) -> bytes: ...
+
+    def root_to_challenge(self, root: bytes, field_id) -> np.ndarray: ...
+
+
+class CudaFriBackend:
+    """The product path: libhodor_b200.so on torch's current stream."""
+
+    def lde_cosets(self, coeffs, log_n, log_factor, coset, first, stride, log_count, field_id):
+        from . import device as dev
+        from ._ffi import check, ensure_init, lib
+
+        ensure_init()
+        out = dev.empty_elems((1 << log_n) << log_count, coeffs.device)
+        check(lib.hodor_cuda_lde_cosets_dev(coeffs.data_ptr(), log_n, log_factor, int(coset), first, stride, log_count,
+                                            out.data_ptr(), field_id, dev._stream()))
+        return out
+
+    def merkle_build(self, leaves, field_id):
+        from . import device as dev
+
+        nodes = torch.empty_like(leaves)
+        dev.merkle_build(leaves, leaves.shape[0], nodes, field_id)
+        return nodes
+
+    def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id):
+        import ctypes as C
+        from . import device as dev
+        from ._ffi import check, ensure_init, lib
+
+        ensure_init()
+        d_chal = dev.to_device(np.ascontiguousarray(challenge, np.uint64).reshape(1, 4), values.device)
+        out = dev.empty_elems(values.shape[0] // 2, values.device)
+        check(lib.hodor_cuda_fri_fold_shard_dev(values.data_ptr(), C.c_uint64(values.shape[0]), C.c_uint64(initial_domain_size),
+                                                layer, log_g, rank, d_chal.data_ptr(), out.data_ptr(), field_id, dev._stream()))
+        return out
+
+    def fri_commit(self, values, lde_factor, out_coeffs, field_id):
+        from . import device as dev
+
+        proto = dev.fri_commit(values.contiguous(), lde_factor, out_coeffs, field_id)
+        res = (proto.get_roots(), proto.challenges.copy(), proto.final_coefficients.copy())
+        proto.free()
+        return res
+
+    def hash_node(self, left, right):
+        from .iop import Blake2sTreeHasher
+
+        return Blake2sTreeHasher.hash_node([left, right])
+
+    def root_to_challenge(self, root, field_id):
+        from .iop import Blake2sLeafEncoder
+
+        return Blake2sLeafEncoder.interpret_hash(field_id, root)
+
+
+def _world(group):
+    if dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def lde_sharded(coeffs: torch.Tensor, log_n: int, log_factor: int, coset: bool, field_id: int, group=None,
+                backend: Optional[FriShardBackend] = None) -> torch.Tensor:
+    """Rank r's cyclic slice v[r + G*tau] of the L-coset LDE; `coeffs` is replicated on every rank."""
+    world, rank = _world(group)
+    log_g = world.bit_length() - 1
+    if world != 1 << log_g or log_g > log_factor:
+        raise ValueError("world size must be a power of two not larger than the blowup factor")
+    backend = backend or CudaFriBackend()
+    return backend.lde_cosets(coeffs, log_n, log_factor, coset, rank, world, log_factor - log_g, field_id)
+
+
+def cyclic_to_block(local: torch.Tensor, group=None) -> torch.Tensor:
+    """All-to-all: cyclic slice v[r + G*tau] -> natural-order block v[q*M/G .. (q+1)*M/G)."""
+    world, _ = _world(group)
+    if world == 1:
+        return local
+    m = local.shape[0]
+    if m % world:
+        raise ValueError("slice too short to re-block")
+    recv = torch.empty_like(local)
+    dist.all_to_all_single(recv, local.contiguous(), group=group)  # chunk q of rank r: tau in [q*m/G, (q+1)*m/G)
+    # recv[r'][t'] = v[r' + G*(q*m/G + t')] = block element r' + G*t'  ->  interleave to (t', r')
+    return recv.view(world, m // world, 4).transpose(0, 1).contiguous().view(m, 4)
+
+
+@dataclass
+class ShardedCommitment:
+    """One committed layer: the local subtree (heap order, local root at [1] = global node G + rank),
+    the top of the tree (global nodes 1 .. 2G-1, identical on every rank) and the layer's root."""
+
+    size: int
+    local_nodes: Optional[torch.Tensor]
+    top_nodes: List[bytes]
+    root: bytes
+
+
+@dataclass
+class ShardedFriPrototype:
+    roots: List[bytes] = field(default_factory=list)
+    challenges: List[np.ndarray] = field(default_factory=list)
+    final_root: bytes = b""
+    final_coefficients: Optional[np.ndarray] = None
+    commitments: List[ShardedCommitment] = field(default_factory=list)  # the layers committed while sharded
+    layer_slices: List[torch.Tensor] = field(default_factory=list)     # this rank's cyclic slice of each of them
+    num_steps: int = 0
+
+
+def merkle_sharded(block_leaves: torch.Tensor, field_id: int, group=None,
+                   backend: Optional[FriShardBackend] = None) -> ShardedCommitment:
+    world, rank = _world(group)
+    backend = backend or CudaFriBackend()
+    nodes = backend.merkle_build(block_leaves, field_id)
+    local_root = nodes[1].cpu().numpy().tobytes()
+    if world == 1:
+        return ShardedCommitment(block_leaves.shape[0], nodes, [b"", local_root], local_root)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local_root, group=group)
+    top = [b""] * (2 * world)
+    for q in range(world):
+        top[world + q] = gathered[q]
+    for i in range(world - 1, 0, -1):
+        top[i] = backend.hash_node(top[2 * i], top[2 * i + 1])
+    return ShardedCommitment(block_leaves.shape[0] * world, nodes, top, top[1])
+
+
+def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor: int, out_coeffs: int, field_id: int,
+                       group=None, backend: Optional[FriShardBackend] = None, gather_below: int = 1 << 16,
+                       keep_layers: bool = True) -> ShardedFriPrototype:
+    """NaiveFriIop::proof_from_lde_by_values (src/fri/fri_on_values.rs:11-159) on an LDE held as
+    cyclic slices.  Returns roots / challenges / final coefficients identical to the unsharded chain."""
+    world, rank = _world(group)
+    log_g = world.bit_length() - 1
+    backend = backend or CudaFriBackend()
+    steps = ((domain_size // lde_factor) // out_coeffs).bit_length() - 1
+    if steps < 1:
+        raise ValueError("zero folding steps (the reference panics here)")
+    if local_cyclic.shape[0] * world != domain_size:
+        raise ValueError("local slice has the wrong length")
+    proto = ShardedFriPrototype(num_steps=steps)
+    values, size, layer = local_cyclic, domain_size, 0
+    gather_below = max(gather_below, 4 * world * world)
+    while True:
+        if size < gather_below or layer >= steps - 1:
+            # finish on every rank with the single-GPU chain, starting at this layer's commitment
+            # (at least one fold is always left for it, so it also produces the final coefficients)
+            if world > 1:
+                parts = [torch.empty_like(values) for _ in range(world)]
+                dist.all_gather(parts, values.contiguous(), group=group)
+                full = torch.stack(parts, dim=1).reshape(size, 4)  # v[r + G*tau] -> natural order
+            else:
+                full = values
+            t_roots, t_chal, tail_final = backend.fri_commit(full, lde_factor, out_coeffs, field_id)
+            proto.roots.extend(bytes(r) for r in t_roots)
+            proto.challenges.extend(np.array(c, dtype=np.uint64) for c in t_chal)
+            break
+        com = merkle_sharded(cyclic_to_block(values, group), field_id, group, backend)
+        proto.roots.append(com.root)
+        if keep_layers:
+            proto.commitments.append(com)
+            proto.layer_slices.append(values)
+        challenge = backend.root_to_challenge(com.root, field_id)
+        proto.challenges.append(challenge)
+        values = backend.fold_shard(values, domain_size, layer, log_g, rank, challenge, field_id)
+        size //= 2
+        layer += 1
+    proto.final_root = proto.roots[-1]
+    proto.final_coefficients = np.array(tail_final, dtype=np.uint64)
+    assert len(proto.roots) == steps + 1 and len(proto.challenges) == steps
+    return proto

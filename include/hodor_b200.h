@@ -152,6 +152,18 @@ int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domai
                             const void* d_challenge, void* d_out, int field_id, void* stream);
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
                                void* stream);
+/* Building blocks for an LDE + FRI commit sharded over G = 2^log_g GPUs (hodor_b200/sharded.py):
+ * - the cosets i = first_coset + coset_stride * t (t < 2^log_count) of the L = 2^log_factor coset LDE,
+ *   interleaved among themselves: d_out[t + 2^log_count * k].  With first = rank, stride = G this is
+ *   exactly rank's cyclic slice v[rank + G * tau] of the full LDE (cosets are independent:
+ *   src/polynomials/mod.rs:572-587), computed with no communication;
+ * - one FRI layer on such a cyclic slice (n_local = layer size / G values): the fold pairs
+ *   (idx, idx + M/2) of src/fri/fri_on_values.rs:74-101 stay on one rank. */
+int hodor_cuda_lde_cosets_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint32_t first_coset,
+                              uint32_t coset_stride, uint32_t log_count, void* d_out, int field_id, void* stream);
+int hodor_cuda_fri_fold_shard_dev(const void* d_in, uint64_t n_local, uint64_t initial_domain_size, uint32_t layer,
+                                  uint32_t log_g, uint32_t rank, const void* d_challenge, void* d_out, int field_id,
+                                  void* stream);
 /* Four-step building blocks for an NTT sharded over G = 2^log_g GPUs (multi-GPU):
  * step A on rank r: n/G-point column NTTs of the rank's slice + twiddle by omega^(j2 * k1);
  * after the all-to-all, step B: row NTTs.  See hodor_b200/sharded.py for the orchestration. */

@@ -397,3 +397,43 @@ def test_sharded_steps_single_gpu(hodor, oracle, world):
         recv = torch.cat([cols[g][h * chunk : (h + 1) * chunk] for g in range(world)]).contiguous()
         outs.append(dev.to_host(be.shard_rows(recv, log_n, log_g, h, omega, fid)))
     assert np.array_equal(gather_output(outs), oracle.serial_fft(fid, a, omega, log_n))
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharded_lde_fri_building_blocks(hodor, oracle, world):
+    """hodor_cuda_lde_cosets_dev / hodor_cuda_fri_fold_shard_dev for every rank of a `world`-GPU box,
+    run in turn on one GPU: rank r's coset subset is the cyclic slice LDE[r::G] and its fold is the
+    cyclic slice of the next layer.  (The collectives are covered by tests/test_sharded_cpu.py and by
+    tools/sharded_check.py under torchrun.)"""
+    from hodor_b200 import device as dev
+    from hodor_b200.sharded_fri import CudaFriBackend
+    fid, log_n, log_f = 0, 13, 3
+    L = 1 << log_f
+    log_g = world.bit_length() - 1
+    be = CudaFriBackend()
+    coeffs = oracle.random_elements(fid, 1 << log_n, seed=808)
+    full = oracle.lde(fid, coeffs, log_n, L, True)
+    proto = oracle.fri_commit(fid, full, L, 1)
+    d_coeffs = dev.to_device(coeffs)
+    for r in range(world):
+        local = be.lde_cosets(d_coeffs, log_n, log_f, True, r, world, log_f - log_g, fid)
+        assert np.array_equal(dev.to_host(local), full[r::world])
+        nxt = be.fold_shard(local, full.shape[0], 0, log_g, r, proto.challenges[0], fid)
+        assert np.array_equal(dev.to_host(nxt), proto.layer_values[0][r::world])
+        nxt2 = be.fold_shard(nxt, full.shape[0], 1, log_g, r, proto.challenges[1], fid)
+        assert np.array_equal(dev.to_host(nxt2), proto.layer_values[1][r::world])
+
+
+def test_sharded_fri_world1_equals_single_gpu_chain(hodor, oracle):
+    from hodor_b200 import device as dev
+    from hodor_b200.sharded_fri import fri_commit_sharded, lde_sharded
+    fid, log_n, log_f = 0, 14, 3
+    coeffs = oracle.random_elements(fid, 1 << log_n, seed=909)
+    local = lde_sharded(dev.to_device(coeffs), log_n, log_f, True, fid)
+    full = oracle.lde(fid, coeffs, log_n, 1 << log_f, True)
+    assert np.array_equal(dev.to_host(local), full)
+    proto = fri_commit_sharded(local, full.shape[0], 1 << log_f, 1, fid, gather_below=1 << 10)
+    want = oracle.fri_commit(fid, full, 1 << log_f, 1)
+    assert proto.roots == want.roots() and len(proto.commitments) >= 5
+    assert np.array_equal(np.stack(proto.challenges), want.challenges)
+    assert np.array_equal(proto.final_coefficients, want.final_coefficients)

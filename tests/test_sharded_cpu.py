@@ -90,3 +90,96 @@ def test_sharded_argument_checks():
     assert [int(x) for x in g[:, 0]] == [0, 0, 1, 1, 0, 0, 1, 1]
     with pytest.raises(ValueError):
         ntt_sharded(torch.zeros((3, 4), dtype=torch.int64), 4, np.zeros(4, np.uint64), 0, backend=OracleBackend())
+
+
+# --------------------------------------------------------------------------------------------------
+# coset LDE + FRI commit chain sharded over ranks (hodor_b200/sharded_fri.py), gloo + oracle double
+# --------------------------------------------------------------------------------------------------
+class OracleFriBackend:
+    """Test double for the CUDA steps of sharded_fri (TEST ONLY: uses oracle/)."""
+
+    def __init__(self):
+        from oracle import oracle as O
+        self.O = O
+
+    @staticmethod
+    def _t(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64).reshape(-1, 4))
+
+    @staticmethod
+    def _n(t):
+        return t.contiguous().numpy().view(np.uint64).reshape(-1, 4)
+
+    def lde_cosets(self, coeffs, log_n, log_factor, coset, first, stride, log_count, field_id):
+        L, cnt, n = 1 << log_factor, 1 << log_count, 1 << log_n
+        full = self.O.lde(field_id, self._n(coeffs), log_n, L, coset)
+        out = np.zeros((n * cnt, 4), np.uint64)
+        for t in range(cnt):
+            out[t::cnt] = full[first + stride * t :: L]
+        return self._t(out)
+
+    def merkle_build(self, leaves, field_id):
+        return self._t(self.O.merkle_create(field_id, self._n(leaves)).reshape(-1))
+
+    def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id):
+        O, v = self.O, self._n(values)
+        half = v.shape[0] // 2
+        log_n0 = initial_domain_size.bit_length() - 1
+        winv = O.inverse(field_id, O.domain_generator(field_id, log_n0))
+        tw = np.stack([O.pow_(field_id, winv, (rank + (t << log_g)) << layer) for t in range(half)])
+        two_inv = O.inverse(field_id, O.to_mont(field_id, O.ints_to_array([2]))[0])
+        f0, f1 = v[:half], v[half:]
+        odd = O.mul(field_id, O.mul(field_id, O.sub(field_id, f0, f1), tw), np.tile(challenge, (half, 1)))
+        return self._t(O.mul(field_id, O.add(field_id, odd, O.add(field_id, f0, f1)), np.tile(two_inv, (half, 1))))
+
+    def fri_commit(self, values, lde_factor, out_coeffs, field_id):
+        p = self.O.fri_commit(field_id, self._n(values), lde_factor, out_coeffs)
+        return p.roots(), p.challenges, p.final_coefficients
+
+    def hash_node(self, left, right):
+        return self.O.hash_node(left, right)
+
+    def root_to_challenge(self, root, field_id):
+        return self.O.interpret_hash(field_id, root)
+
+
+def _fri_worker(rank, world, port, log_n, log_factor, out_coeffs, gather_below, result_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hodor_b200.sharded_fri import cyclic_to_block, fri_commit_sharded, lde_sharded
+        from oracle import oracle as O
+        be = OracleFriBackend()
+        coeffs = O.random_elements(0, 1 << log_n, seed=99)
+        local = lde_sharded(be._t(coeffs), log_n, log_factor, True, 0, backend=be)
+        block = cyclic_to_block(local)
+        proto = fri_commit_sharded(local, (1 << log_n) << log_factor, 1 << log_factor, out_coeffs, 0, backend=be,
+                                   gather_below=gather_below)
+        np.savez(os.path.join(result_dir, f"fri{rank}.npz"), local=be._n(local), block=be._n(block),
+                 roots=np.frombuffer(b"".join(proto.roots), np.uint8), challenges=np.stack(proto.challenges),
+                 final=proto.final_coefficients, sharded_layers=len(proto.commitments))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n,log_factor,gather_below", [(2, 5, 3, 16), (4, 6, 2, 64), (2, 4, 1, 1 << 16)])
+def test_sharded_lde_and_fri_chain_over_gloo(oracle, tmp_path, world, log_n, log_factor, gather_below):
+    out_coeffs = 2
+    mp.spawn(_fri_worker, args=(world, _free_port(), log_n, log_factor, out_coeffs, gather_below, str(tmp_path)),
+             nprocs=world, join=True)
+    coeffs = oracle.random_elements(0, 1 << log_n, seed=99)
+    L = 1 << log_factor
+    full = oracle.lde(0, coeffs, log_n, L, True)
+    want = oracle.fri_commit(0, full, L, out_coeffs)
+    m = full.shape[0] // world
+    for r in range(world):
+        res = np.load(tmp_path / f"fri{r}.npz")
+        assert np.array_equal(res["local"], full[r::world])            # cyclic slice, no communication
+        assert np.array_equal(res["block"], full[r * m : (r + 1) * m])  # after the all-to-all
+        assert res["roots"].tobytes() == b"".join(want.roots())
+        assert np.array_equal(res["challenges"], want.challenges)
+        assert np.array_equal(res["final"], want.final_coefficients)
+        if gather_below <= 64:
+            assert int(res["sharded_layers"]) >= 2  # several layers really ran distributed
