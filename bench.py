@@ -362,6 +362,33 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                             "hbm_frac_aggregate": 64 * (1 << ln) / (ms * 1e-3) / 1e9 / (peak_gbs * world)})
             del local
 
+    # ---- the north-star target: ONE 2^24 -> 2^28 coset LDE + full FRI commit chain over all ranks
+    # (cosets sharded with no communication; one NCCL all-to-all per committed FRI layer)
+    sharded_fri = None
+    if world > 1 and world <= 16:
+        from hodor_b200.sharded_fri import fri_commit_sharded, lde_sharded
+        s_log_f = 4
+        d_shared = dev.to_device(synthetic_elements(n, seed=4000))  # replicated coefficient vector
+
+        def lde_fri():
+            loc = lde_sharded(d_shared, LOG_N, s_log_f, True, FIELD)
+            return fri_commit_sharded(loc, n << s_log_f, 1 << s_log_f, 1, FIELD, keep_layers=False)
+
+        lde_fri()
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(2, args.steps // 2)
+        for _ in range(reps):
+            pr = lde_fri()
+        torch.cuda.synchronize()
+        s_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / reps
+        sharded_fri = {"workload": f"coset LDE 2^{LOG_N} -> 2^{LOG_N + s_log_f} + FRI commit chain ({pr.num_steps} layers, "
+                                   f"{pr.num_steps + 1} Merkle trees) sharded over {world} GPUs", "ms": s_ms,
+                       "lde_elems_per_s": (n << s_log_f) / (s_ms * 1e-3), "scaling": "strong",
+                       "collective": "NCCL all_to_all_single per committed layer (cyclic -> block), all_gather of sub-roots",
+                       "timer": "host perf_counter, barrier + synchronize both sides, max over ranks"}
+        del d_shared
+
     sweep = None
     if args.sweep and world == 1:
         sweep = []
@@ -398,6 +425,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         }
         if sharded is not None:
             line["sharded_ntt"] = {"collective": "NCCL all_to_all_single (one transpose)", "scaling": "strong", "sizes": sharded}
+        if sharded_fri is not None:
+            line["sharded_lde_fri"] = sharded_fri
         if sweep is not None:
             line["ntt_sweep"] = sweep
         emit(line)
