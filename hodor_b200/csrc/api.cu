@@ -241,6 +241,7 @@ int hodor_cuda_init(int device) {
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaMalloc((void**)&c->small, 4096));
     c->key = b2s_keyed_state();
+    if (const char* mb = getenv("HODOR_TABLE_BUDGET_MB")) c->full_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
     g_ctx = c.release();
     return HODOR_OK;
 }
@@ -260,6 +261,7 @@ void hodor_cuda_shutdown(void) {
     for (int i = 0; i < 2; i++)
         if (g_ctx->io[i]) cudaFree(g_ctx->io[i]);
     for (auto& b : g_ctx->pool_free_list) cudaFree(b.first);
+    for (auto& kv : g_ctx->full_tables) cudaFree(kv.second.first);
     for (auto& r : g_ctx->prof) {
         cudaEventDestroy(r.start);
         cudaEventDestroy(r.stop);
@@ -275,7 +277,7 @@ const char* hodor_cuda_last_error(void) { return g_last_error.c_str(); }
 
 size_t hodor_cuda_workspace_bytes(void) {
     Ctx* c = g_ctx;
-    return c ? c->ws_bytes + c->table_bytes + c->io_bytes[0] + c->io_bytes[1] : 0;
+    return c ? c->ws_bytes + c->table_bytes + c->full_bytes + c->io_bytes[0] + c->io_bytes[1] : 0;
 }
 
 uint64_t hodor_cuda_launch_count(void) {

@@ -75,6 +75,11 @@ struct Ctx {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> event_pool;
 
+    // expanded (one entry per element) twiddle / coset-power tables; bounded by full_budget bytes
+    std::map<std::string, std::pair<uint4*, size_t>> full_tables;
+    size_t full_bytes = 0;
+    size_t full_budget = (size_t)12 << 30;  // HODOR_TABLE_BUDGET_MB overrides; 0 disables
+
     std::vector<std::pair<void*, size_t>> pool_free_list;
     std::map<void*, size_t> pool_live;
     void* pool_alloc(size_t bytes);

@@ -165,6 +165,9 @@ struct Ops {
         c.pow_tables.clear();
         c.ntt_tables.clear();
         c.table_bytes = 0;
+        for (auto& kv : c.full_tables) cudaFree(kv.second.first);
+        c.full_tables.clear();
+        c.full_bytes = 0;
     }
 
     static int get_pow_tables(Ctx& c, const PowTables** out, const std::vector<Fe>& bases, uint32_t bits, const Fe* scale,
@@ -270,6 +273,35 @@ struct Ops {
         }
         *out = &it->second;
         return HODOR_OK;
+    }
+
+    // One entry per element instead of hi * lo: trades HBM capacity and (abundant) bandwidth for one
+    // Montgomery multiplication per element -- the path is multiplier bound, not HBM bound.  Returns
+    // null (callers fall back to the two-level tables) when the budget would be exceeded.
+    static const uint4* get_full_table(Ctx& c, const std::string& key, const TwoLevel& src, uint32_t stride_lo,
+                                       uint32_t stride_hi, size_t n, uint32_t count, int boundary_s, cudaStream_t st) {
+        auto it = c.full_tables.find(key);
+        if (it != c.full_tables.end()) return it->second.first;
+        const size_t bytes = n * count * sizeof(Fe);
+        if (c.full_budget == 0 || c.full_bytes + bytes > c.full_budget) return nullptr;
+        uint4* d = nullptr;
+        if (cudaMalloc((void**)&d, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        const unsigned gx = (unsigned)((n + 255) / 256 > 148 * 32 ? 148 * 32 : (n + 255) / 256);
+        {
+            ProfScope ps(c, st, "expand_table");
+            expand_table_kernel<F><<<dim3(gx, count), 256, 0, st>>>(d, src, stride_lo, stride_hi, n, boundary_s, 0u);
+        }
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(d);
+            return nullptr;
+        }
+        c.full_tables.emplace(key, std::make_pair(d, bytes));
+        c.full_bytes += bytes;
+        return d;
     }
 
     // ------------------------------------------------------------------ transforms
@@ -428,6 +460,31 @@ struct Ops {
             p.coset_stride_hi = coset->stride_hi();
         }
         for (int k = 0; k < 7; k++) p.wr[k] = tw->wr[k];
+        // expanded tables for the transforms where they pay (>= 2^20): pass-1 inter-pass twiddles and
+        // the per-coset scaling powers, one entry per element
+        const uint4* tw_full = nullptr;
+        const uint4* coset_full = nullptr;
+        if (log_n >= 20) {
+            const uint32_t s0 = log_n - plan.b[0];
+            // make room once, before any pointer is handed out: drop every expanded table if this
+            // call's tables would not fit beside the cached ones
+            const std::string bkey = key_of("bfull", log_n, s0, &omega, 1);
+            const size_t want = (c.full_tables.count(bkey) ? 0 : n * sizeof(Fe)) + (coset ? n * L * sizeof(Fe) : 0);
+            if (c.full_bytes + want > c.full_budget && !c.full_tables.empty()) {
+                cudaDeviceSynchronize();
+                for (auto& kv : c.full_tables) cudaFree(kv.second.first);
+                c.full_tables.clear();
+                c.full_bytes = 0;
+            }
+            tw_full = get_full_table(c, key_of("bfull", log_n, s0, &omega, 1), tw->pw.two_level(), 0, 0, n, 1, (int)s0, st);
+            if (coset) {
+                std::vector<Fe> kb{*shift0};
+                if (step) kb.push_back(*step);
+                coset_full = get_full_table(c, key_of("cfull", log_n, log_l, kb.data(), (int)kb.size()), coset->two_level(),
+                                            coset->stride_lo(), coset->stride_hi(), n, L, -1, st);
+            }
+        }
+        p.coset_full = coset_full;
         uint32_t below = log_n;
         for (int i = 0; i < plan.passes; i++) {
             const int b = plan.b[i];
@@ -435,6 +492,7 @@ struct Ops {
             const bool last = (i == plan.passes - 1);
             p.s = below;
             p.tw_b = tw->tw_b[b];
+            p.tw_full = (i == 0 && !last) ? tw_full : nullptr;
             p.tw_direct = (!last && below + b <= 16) ? tw->tw_direct[below + b] : nullptr;
             p.tw_shift = log_n - below - b;
             p.flags = last ? flags : 0;

@@ -49,6 +49,12 @@ struct NttPass {
     TwoLevel tw;        // powers of omega
     const uint4* tw_b;  // omega_B^x, x in [0, 2^B)
     const uint4* tw_direct;  // inter-pass twiddles omega_N^x, x in [0, N = 2^(s+B)), when N <= 2^16; else null
+    // Expanded tables (the GPU counterpart of the reference's PrecomputedOmegas, src/precomputations/
+    // mod.rs:14-66), streamed with the same coalesced addressing as the data; null => multiply two
+    // table entries instead.  tw_full[(k << s) + r] = omega^(k * r) for pass 1 (n entries);
+    // coset_full[i * n + j] = shift_i^j (L * n entries).
+    const uint4* tw_full;
+    const uint4* coset_full;
     TwoLevel coset;     // pass 1 of a scaled transform: shift_i^j tables, coset i at +i*coset_stride
     TwoLevel out_pow;   // PASS_OUT_POW
     Fe out_const;       // PASS_OUT_CONST
@@ -237,8 +243,10 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
             Fe v = ld_fe(p.in, idx);
             if constexpr (SCALE_IN) {
                 // j = idx (u == 0 in pass 1): a[j] * shift_i^j
-                const Fe w = two_level_pow(fld, p.coset, (size_t)coset_hi * p.coset_stride_lo,
-                                           (size_t)coset_hi * p.coset_stride_hi, idx);
+                Fe w;
+                if (p.coset_full != nullptr) w = ld_fe(p.coset_full, (size_t)coset_hi * n + idx);
+                else w = two_level_pow(fld, p.coset, (size_t)coset_hi * p.coset_stride_lo,
+                                       (size_t)coset_hi * p.coset_stride_hi, idx);
                 v = fld.mul(v, w);
             }
             return v;
@@ -257,7 +265,8 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
             // (2 MiB at N = 2^16, L2 resident), else hi * lo from the two-level tables (one more multiply)
             const uint64_t prod = (uint64_t)kloc * (col0 + c);
             Fe w;
-            if (p.tw_direct != nullptr) w = ld_fe(p.tw_direct, (size_t)prod);
+            if (p.tw_full != nullptr) w = ld_fe(p.tw_full, ((size_t)kloc << p.s) + col0 + c);
+            else if (p.tw_direct != nullptr) w = ld_fe(p.tw_direct, (size_t)prod);
             else w = two_level_pow(fld, p.tw, 0, 0, prod << p.tw_shift);
             v = fld.mul(v, w);
             st_fe(p.out, out_base + ((size_t)kloc << p.s) + c, v);
@@ -348,6 +357,21 @@ __global__ void pow_table_kernel(uint4* out, const Fe* bases, const Fe* scale, u
     Fe r = fld.pow(bases[blockIdx.y], i);
     if (scale != nullptr) r = fld.mul(r, scale[0]);
     st_fe(out, (size_t)blockIdx.y * count + i, r);
+}
+
+// Expanded tables.  out[b * n + j] = bases_b^j  (coset scaling for every coset b), or with
+// `boundary_s` >= 0: out[idx] = omega^((idx >> s) * (idx & (2^s - 1))), the pass-1 inter-pass twiddle
+// stored at the address of the element it multiplies.
+template <class F>
+__global__ void expand_table_kernel(uint4* out, TwoLevel t, uint32_t stride_lo, uint32_t stride_hi, size_t n,
+                                    int boundary_s, uint32_t zero) {
+    const Field<F> fld(threadIdx.x & zero);
+    const size_t b = blockIdx.y;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        uint64_t e = j;
+        if (boundary_s >= 0) e = (uint64_t)(j >> boundary_s) * (j & (((size_t)1 << boundary_s) - 1));
+        st_fe(out, b * n + j, two_level_pow(fld, t, b * stride_lo, b * stride_hi, e));
+    }
 }
 
 // a[j] <- a[j] * c * g^j     (distribute_powers, src/fft/mod.rs:110-123; c folded into pw.lo)
