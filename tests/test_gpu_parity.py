@@ -424,6 +424,40 @@ def test_sharded_lde_fri_building_blocks(hodor, oracle, world):
         assert np.array_equal(dev.to_host(nxt2), proto.layer_values[1][r::world])
 
 
+def test_two_level_fallback_for_large_transforms(oracle):
+    """Transforms >= 2^20 normally stream expanded (one entry per element) twiddle / coset tables; with
+    HODOR_TABLE_BUDGET_MB=0 the same sizes must take the two-level (hi * lo) path and agree bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import numpy as np, hodor_b200 as H\n"
+        "from oracle import oracle as O\n"
+        "H.init(0)\n"
+        "a = O.random_elements(0, 1 << 20, seed=321)\n"
+        "got = H.Polynomial.from_coeffs(0, a).coset_lde(None, 2).as_ref()\n"
+        "assert np.array_equal(got, O.lde(0, a, 20, 2, True)), 'lde'\n"
+        "assert np.array_equal(H.Polynomial.from_coeffs(0, a).fft().as_ref(), O.fft(0, a, 20)), 'fft'\n"
+        "from hodor_b200 import _ffi\n"
+        "print('tables', _ffi.lib.hodor_cuda_workspace_bytes())\n"
+    )
+    for budget in ("0", "4096"):
+        env = dict(os.environ, HODOR_TABLE_BUDGET_MB=budget, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_lde_cosets_argument_errors(hodor, oracle):
+    from hodor_b200 import _ffi, device as dev
+    d = dev.to_device(oracle.random_elements(0, 16, 1))
+    out = dev.empty_elems(64)
+    lib = _ffi.lib
+    assert lib.hodor_cuda_lde_cosets_dev(d.data_ptr(), 4, 2, 1, 3, 2, 1, out.data_ptr(), 0, None) == _ffi.ERR_INVALID_ARG  # 3 + 2 >= 4
+    assert lib.hodor_cuda_lde_cosets_dev(d.data_ptr(), 4, 2, 1, 0, 1, 3, out.data_ptr(), 0, None) == _ffi.ERR_INVALID_ARG  # count > L
+    assert lib.hodor_cuda_lde_cosets_dev(d.data_ptr(), 4, 30, 1, 0, 1, 0, out.data_ptr(), 0, None) == _ffi.ERR_DOMAIN
+
+
 def test_sharded_fri_world1_equals_single_gpu_chain(hodor, oracle):
     from hodor_b200 import device as dev
     from hodor_b200.sharded_fri import fri_commit_sharded, lde_sharded
