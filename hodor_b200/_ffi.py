@@ -18,6 +18,7 @@ ERR_DOMAIN = -2
 ERR_CUDA = -3
 ERR_OOM = -4
 ERR_NOT_A_ROOT = -5
+ERR_NOT_INVERTIBLE = -6
 
 BLS12_381_FR = 0  # what the reference's src/bn256.rs declares
 BN254_FR = 1
@@ -82,6 +83,8 @@ _SIGS = {
     "hodor_cuda_distribute_powers": (C.c_int, [u64p, C.c_uint64, u64p, C.c_int]),
     "hodor_cuda_lde": (C.c_int, [u64p, C.c_uint32, C.c_uint32, C.c_int, u64p, C.c_int]),
     "hodor_cuda_elementwise": (C.c_int, [C.c_int, u64p, u64p, u64p, C.c_uint64, C.c_int]),
+    "hodor_cuda_batch_inversion": (C.c_int, [u64p, C.c_uint64, C.c_int]),
+    "hodor_cuda_evaluate_at": (C.c_int, [u64p, C.c_uint64, u64p, u64p, C.c_int]),
     "hodor_cuda_merkle_build": (C.c_int, [u64p, C.c_uint64, u8p, C.c_int]),
     "hodor_cuda_fri_commit": (vp, [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "hodor_cuda_fri_free": (None, [vp]),
@@ -103,6 +106,8 @@ _SIGS = {
     "hodor_cuda_lde_cosets_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                             C.c_int, vp]),
     "hodor_cuda_elementwise_dev": (C.c_int, [C.c_int, vp, vp, vp, C.c_uint64, C.c_int, vp]),
+    "hodor_cuda_batch_inversion_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),
+    "hodor_cuda_evaluate_at_dev": (C.c_int, [vp, C.c_uint64, u64p, vp, C.c_int, vp]),
     "hodor_cuda_ntt_shard_cols_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_int, vp]),
     "hodor_cuda_ntt_shard_rows_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_int, vp]),
 }
@@ -124,7 +129,7 @@ def check(rc: int) -> int:
     if rc is None or rc >= 0:
         return rc
     msg = last_error()
-    if rc == ERR_DOMAIN:
+    if rc in (ERR_DOMAIN, ERR_NOT_INVERTIBLE):  # the reference returns Err(SynthesisError::Error) for both
         raise SynthesisError(rc, msg)
     raise HodorError(rc, msg)
 

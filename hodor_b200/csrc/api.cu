@@ -517,6 +517,18 @@ int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d
     GET_OPS(field_id);
     return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, pick_stream(c, stream));
 }
+int hodor_cuda_batch_inversion_dev(void* d_a, uint64_t n, int* d_status, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (d_status == nullptr) return fail(HODOR_ERR_INVALID_ARG, "batch_inversion: d_status is NULL");
+    return ops->batch_inversion(*c, (uint4*)d_a, (size_t)n, d_status, pick_stream(c, stream));
+}
+int hodor_cuda_evaluate_at_dev(const void* d_coeffs, uint64_t n, const uint64_t g[4], void* d_out, int field_id,
+                               void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return ops->evaluate_at(*c, (const uint4*)d_coeffs, (size_t)n, fe_from_u64(g), (uint4*)d_out, pick_stream(c, stream));
+}
 int hodor_cuda_ntt_shard_cols_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
                                   const uint64_t omega[4], int field_id, void* stream) {
     LOCKED_CTX();
@@ -622,6 +634,37 @@ int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_
     rc = ops->elementwise(*c, op, (const uint4*)c->io[0], (const uint4*)c->io[1], (uint4*)c->io[0], n, c->stream);
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[0], n * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+int hodor_cuda_batch_inversion(uint64_t* a, uint64_t n, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (n == 0) return HODOR_OK;
+    int rc = c->ensure_io(0, n * 32);
+    if (rc) return rc;
+    int* d_status = (int*)(c->small + 64);  // scalar scratch, beyond the slots the FRI chain uses
+    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = ops->batch_inversion(*c, (uint4*)c->io[0], (size_t)n, d_status, c->stream);
+    if (rc) return rc;
+    int status = 0;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (status != 0) return fail(HODOR_ERR_NOT_INVERTIBLE, "batch_inversion: the vector contains zero");
+    HODOR_CUDA_TRY(cudaMemcpyAsync(a, c->io[0], n * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+int hodor_cuda_evaluate_at(const uint64_t* coeffs, uint64_t n, const uint64_t g[4], uint64_t out[4], int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    int rc = c->ensure_io(0, (n ? n : 1) * 32);
+    if (rc) return rc;
+    uint4* d_out = c->small + 66;
+    if (n) HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], coeffs, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = ops->evaluate_at(*c, (const uint4*)c->io[0], (size_t)n, fe_from_u64(g), d_out, c->stream);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(out, d_out, 32, cudaMemcpyDeviceToHost, c->stream));
     HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return HODOR_OK;
 }

@@ -41,11 +41,12 @@ struct PowTables {
 
 struct NttTables {
     PowTables pw;            // powers of omega, exponents [0, 2^log_n)
+    // tw_b and tw_direct entries are FePre (64 B): read directly as multipliers
     uint4* tw_b[10] = {};    // tw_b[B][x] = omega^(x << (log_n - B)), B in 6..9 (as used by the plan)
     uint4* tw_b_block = nullptr;
     uint4* tw_direct[17] = {};  // tw_direct[k][x] = omega^(x << (log_n - k)), x < 2^k: flat inter-pass twiddles, k <= 16
     uint4* tw_direct_block = nullptr;
-    Fe wr[7];                // omega_16^k, k = 1..7
+    FePre wr[7];             // omega_16^k, k = 1..7, fixed-operand form
     size_t bytes = 0;
 };
 
@@ -144,6 +145,8 @@ struct FieldOps {
                const Fe* step, int out_mode, const Fe* out_g, cudaStream_t st);
     int (*scale_pow)(Ctx&, uint4* a, size_t n, const Fe& g, cudaStream_t st);
     int (*elementwise)(Ctx&, int op, const uint4* a, const uint4* b, uint4* out, size_t n, cudaStream_t st);
+    int (*batch_inversion)(Ctx&, uint4* a, size_t n, int* d_status, cudaStream_t st);
+    int (*evaluate_at)(Ctx&, const uint4* a, size_t n, const Fe& g, uint4* d_out, cudaStream_t st);
     int (*merkle_tail)(Ctx&, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
                        cudaStream_t st);
     int (*fri_fold)(Ctx&, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,

@@ -51,6 +51,11 @@ struct BlsFr {  // what the reference's src/bn256.rs declares: the BLS12-381 sca
                                    0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
         return t[i];
     }
+    HD static constexpr uint32_t NINV256(int i) {  // -p^-1 mod 2^256 (mul_pre operand derivation)
+        constexpr uint32_t t[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfdu, 0x53ba5bffu, 0x0004ec06u, 0x181b2c17u, 0xd7bf2839u, 0x3d443ab0u};
+        return t[i];
+    }
+    HD static constexpr uint32_t NP(int i) { return i == 0 ? 0u - P(0) : ~P(i); }  // 2^256 - p (p odd)
 };
 
 struct Bn254Fr {  // the field usually called "bn256 Fr" (not what src/bn256.rs holds)
@@ -72,6 +77,11 @@ struct Bn254Fr {  // the field usually called "bn256 Fr" (not what src/bn256.rs 
                                    0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
         return t[i];
     }
+    HD static constexpr uint32_t NINV256(int i) {  // -p^-1 mod 2^256 (mul_pre operand derivation)
+        constexpr uint32_t t[8] = {0xefffffffu, 0xc2e1f593u, 0x4c6911b3u, 0x6586864bu, 0x99062391u, 0xe39a9828u, 0x0d8341b2u, 0x73f82f1du};
+        return t[i];
+    }
+    HD static constexpr uint32_t NP(int i) { return i == 0 ? 0u - P(0) : ~P(i); }  // 2^256 - p (p odd)
 };
 
 struct Stark252 {  // src/experiments/mod.rs:18-21
@@ -93,6 +103,11 @@ struct Stark252 {  // src/experiments/mod.rs:18-21
                                    0xff6f8000u, 0xffffffffu, 0x5e008810u, 0x07ffd4abu};
         return t[i];
     }
+    HD static constexpr uint32_t NINV256(int i) {  // -p^-1 mod 2^256 (mul_pre operand derivation)
+        constexpr uint32_t t[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x00000010u, 0x08000000u};
+        return t[i];
+    }
+    HD static constexpr uint32_t NP(int i) { return i == 0 ? 0u - P(0) : ~P(i); }  // 2^256 - p (p odd)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -323,6 +338,7 @@ HD uint32_t sub256(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)
 
 }  // namespace hodor
 #include "mont_split.cuh"
+#include "shoup_rows.cuh"
 namespace hodor {
 
 // ---------------------------------------------------------------------------------------------
@@ -539,6 +555,104 @@ struct Field {
     }
 
     HD Fe sqr(const Fe& a) const { return mul(a, a); }
+
+    // -----------------------------------------------------------------------------------------
+    // Multiplication by a FIXED operand with a precomputed quotient ("Shoup" form).  Every multiply
+    // of the transform kernels is by a table entry (twiddle, coset power, n^-1), so the table holds
+    //     w  = the plain integer value of the factor  (a_mont * w mod p is (a*w) in Montgomery form)
+    //     wq = floor(w * 2^256 / p)
+    // and   q = floor(a * wq / 2^256),   r = a*w - q*p  in [0, 2p)   for every a < 2^256
+    // (w*2^256 = wq*p + eps, a*wq = q*2^256 + delta  =>  r = (delta*p + a*eps) / 2^256 < 2p).
+    // Cost: the HIGH half of one product and the LOW halves of two (the second by the compile-time
+    // words of -p), 36+7 / 28+8 / <= 28+8 32-bit products instead of Montgomery's 64 + 64 + 8.
+    // Only words >= 7 of a*wq are formed (shoup_rows.cuh); what is dropped, D, is < 14 * 2^224, so
+    // the truncation can change q only when the guard word (word 7) is within 14 of wrapping: then
+    // (about 3 in 10^9 multiplies) the exact carry is recomputed out of line.  Result canonical,
+    // bit-identical to mul(a, to_mont(w)).
+    // -----------------------------------------------------------------------------------------
+    static constexpr uint32_t PRE_GUARD = 0xfffffff2u;  // 2^32 - 14
+
+    // floor(D / 2^224) for the dropped part D of a*b (products with i+j <= 5 and the low words of i+j = 6)
+    HD static uint32_t pre_dropped_carry(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        uint64_t carry = 0;  // running value of the columns below, divided by 2^(32*col)
+        for (int col = 0; col <= 6; col++) {
+            uint64_t lo = carry & 0xffffffffu, hi = carry >> 32;
+            for (int i = 0; i <= col; i++) {
+                const uint64_t prod = (uint64_t)a[i] * b[col - i];
+                lo += prod & 0xffffffffu;
+                if (col < 6) hi += prod >> 32;  // column 6's high words were kept (they are in word 7)
+            }
+            carry = hi + (lo >> 32);
+        }
+        return (uint32_t)carry;  // < 14
+    }
+#ifdef __CUDA_ARCH__
+    static __device__ __noinline__ uint32_t pre_dropped_carry_slow(Fe a, Fe b) { return pre_dropped_carry(a.v, b.v); }
+#endif
+
+    template <uint32_t GUARD = PRE_GUARD>
+    HD Fe mul_pre(const Fe& a, const Fe& w, const Fe& wq) const {
+        Fe r;
+#ifdef __CUDA_ARCH__
+        uint32_t q[8], guard;
+        shoup_hi_trunc(q, guard, a.v, wq.v);
+        if (guard >= GUARD) {
+            const uint32_t c = (uint32_t)(((uint64_t)guard + pre_dropped_carry_slow(a, wq)) >> 32);
+            uint32_t cv[8] = {c, 0, 0, 0, 0, 0, 0, 0};
+            add256(q, q, cv);
+        }
+        shoup_lo2<F>(r.v, a.v, w.v, q);
+#else
+        // host: the same integers by plain 64-bit arithmetic (exact q, no truncation)
+        uint32_t t[16] = {0};
+        for (int i = 0; i < 8; i++) {
+            uint64_t c = 0;
+            for (int j = 0; j < 8; j++) {
+                c += (uint64_t)a.v[i] * wq.v[j] + t[i + j];
+                t[i + j] = (uint32_t)c;
+                c >>= 32;
+            }
+            t[i + 8] = (uint32_t)c;
+        }
+        uint32_t acc[8] = {0};
+        for (int pass = 0; pass < 2; pass++) {  // acc = a*w + q*NP mod 2^256
+            for (int i = 0; i < 8; i++) {
+                uint64_t c = 0;
+                for (int j = 0; i + j < 8; j++) {
+                    const uint32_t x = pass == 0 ? a.v[i] : t[8 + i];
+                    const uint32_t y = pass == 0 ? w.v[j] : F::NP(j);
+                    c += (uint64_t)x * y + acc[i + j];
+                    acc[i + j] = (uint32_t)c;
+                    c >>= 32;
+                }
+            }
+        }
+        for (int i = 0; i < 8; i++) r.v[i] = acc[i];
+#endif
+        reduce_once(r.v);
+        return r;
+    }
+
+    // (w, wq) from the Montgomery form of the factor: w = w_mont / R, and since
+    // w * 2^256 = wq * p + w_mont exactly, wq = w_mont * (-p^-1) mod 2^256.
+    HD void make_pre(const Fe& w_mont, Fe& w, Fe& wq) const {
+        w = from_mont(w_mont);
+        uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t c = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (i + j < 8) {
+                    c += (uint64_t)w_mont.v[i] * F::NINV256(j) + acc[i + j];
+                    acc[i + j] = (uint32_t)c;
+                    c >>= 32;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) wq.v[i] = acc[i];
+    }
 
     // plain integer (< p) -> Montgomery (ff_ce from_repr) and back (into_repr)
     HD Fe to_mont(const Fe& a) const { return mul(a, r2()); }

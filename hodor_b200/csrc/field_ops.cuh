@@ -8,6 +8,7 @@
 #include "fri.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "polyops.cuh"
 
 namespace hodor {
 
@@ -199,7 +200,7 @@ struct Ops {
                 const Fe w16 = pow2k(omega, log_n - 4);
                 Fe acc = w16;
                 for (int k = 0; k < 7; k++) {
-                    t.wr[k] = acc;
+                    f.make_pre(acc, t.wr[k].w, t.wr[k].q);
                     acc = f.mul(acc, w16);
                 }
             }
@@ -210,7 +211,7 @@ struct Ops {
                 for (int i = 0; i < plan.passes; i++) need[plan.b[i]] = true;
                 for (int b = 6; b <= 9; b++)
                     if (need[b]) total += (size_t)1 << b;
-                t.bytes = total * sizeof(Fe);
+                t.bytes = total * sizeof(FePre);
                 HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_b_block, t.bytes));
                 Fe* d_base = nullptr;  // device copy of the per-B bases
                 HODOR_CUDA_TRY(cudaMalloc((void**)&d_base, 4 * sizeof(Fe)));
@@ -227,9 +228,9 @@ struct Ops {
                     const uint32_t cnt = 1u << b;
                     {
                         ProfScope ps(c, st, "pow_table");
-                        pow_table_kernel<F><<<dim3((cnt + 255) / 256, 1), 256, 0, st>>>(cur, d_base + nb, nullptr, cnt, 0u);
+                        pow_table_kernel<F, true><<<dim3((cnt + 255) / 256, 1), 256, 0, st>>>(cur, d_base + nb, nullptr, cnt, 0u);
                     }
-                    cur += 2 * (size_t)cnt;
+                    cur += 4 * (size_t)cnt;
                     nb++;
                 }
                 HODOR_CUDA_TRY(cudaGetLastError());
@@ -247,7 +248,7 @@ struct Ops {
                     }
                 }
                 if (dtotal) {
-                    HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_direct_block, dtotal * sizeof(Fe)));
+                    HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_direct_block, dtotal * sizeof(FePre)));
                     uint4* dcur = t.tw_direct_block;
                     for (uint32_t k = 0; k <= 16; k++) {
                         if (t.tw_direct[k] == nullptr) continue;
@@ -258,13 +259,13 @@ struct Ops {
                         const uint32_t cnt = 1u << k;
                         {
                             ProfScope ps(c, st, "pow_table");
-                            pow_table_kernel<F><<<dim3((cnt + 255) / 256, 1), 256, 0, st>>>(dcur, d_base, nullptr, cnt, 0u);
+                            pow_table_kernel<F, true><<<dim3((cnt + 255) / 256, 1), 256, 0, st>>>(dcur, d_base, nullptr, cnt, 0u);
                         }
                         HODOR_CUDA_TRY(cudaStreamSynchronize(st));
-                        dcur += 2 * (size_t)cnt;
+                        dcur += 4 * (size_t)cnt;
                     }
                     HODOR_CUDA_TRY(cudaGetLastError());
-                    t.bytes += dtotal * sizeof(Fe);
+                    t.bytes += dtotal * sizeof(FePre);
                 }
                 cudaFree(d_base);
                 c.table_bytes += t.bytes;
@@ -275,14 +276,15 @@ struct Ops {
         return HODOR_OK;
     }
 
-    // One entry per element instead of hi * lo: trades HBM capacity and (abundant) bandwidth for one
-    // Montgomery multiplication per element -- the path is multiplier bound, not HBM bound.  Returns
+    // One entry per element instead of hi * lo, in the fixed-operand form of Field::mul_pre (64 B per
+    // entry): trades HBM capacity and (abundant) bandwidth for one Montgomery multiplication per
+    // element and a cheaper remaining one -- the path is multiplier bound, not HBM bound.  Returns
     // null (callers fall back to the two-level tables) when the budget would be exceeded.
     static const uint4* get_full_table(Ctx& c, const std::string& key, const TwoLevel& src, uint32_t stride_lo,
                                        uint32_t stride_hi, size_t n, uint32_t count, int boundary_s, cudaStream_t st) {
         auto it = c.full_tables.find(key);
         if (it != c.full_tables.end()) return it->second.first;
-        const size_t bytes = n * count * sizeof(Fe);
+        const size_t bytes = n * count * sizeof(FePre);
         if (c.full_budget == 0 || c.full_bytes + bytes > c.full_budget) return nullptr;
         uint4* d = nullptr;
         if (cudaMalloc((void**)&d, bytes) != cudaSuccess) {
@@ -452,7 +454,7 @@ struct Ops {
         p.b1 = plan.b[0];
         p.zero = 0;
         p.tw = tw->pw.two_level();
-        p.out_const = out_const;
+        f.make_pre(out_const, p.out_const.w, p.out_const.q);
         if (out_pow) p.out_pow = out_pow->two_level();
         if (coset) {
             p.coset = coset->two_level();
@@ -469,7 +471,7 @@ struct Ops {
             // make room once, before any pointer is handed out: drop every expanded table if this
             // call's tables would not fit beside the cached ones
             const std::string bkey = key_of("bfull", log_n, s0, &omega, 1);
-            const size_t want = (c.full_tables.count(bkey) ? 0 : n * sizeof(Fe)) + (coset ? n * L * sizeof(Fe) : 0);
+            const size_t want = (c.full_tables.count(bkey) ? 0 : n * sizeof(FePre)) + (coset ? n * L * sizeof(FePre) : 0);
             if (c.full_bytes + want > c.full_budget && !c.full_tables.empty()) {
                 cudaDeviceSynchronize();
                 for (auto& kv : c.full_tables) cudaFree(kv.second.first);
@@ -544,6 +546,76 @@ struct Ops {
         return HODOR_OK;
     }
 
+    // ------------------------------------------------------------------ batch inversion, evaluation
+    // a[i] <- a[i]^-1 in place; *d_status (device int) = 1 and `a` untouched when some a[i] == 0
+    static int batch_inversion(Ctx& c, uint4* a, size_t n, int* d_status, cudaStream_t st) {
+        if (n == 0) {
+            HODOR_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+            return HODOR_OK;
+        }
+        // level l: m[l] inputs -> M[l] = ceil(m[l] / K) totals, which are level l+1's inputs
+        std::vector<size_t> m{n};
+        while (m.back() > 1) m.push_back((m.back() + BINV_K - 1) / BINV_K);
+        const int levels = (int)m.size() - 1;  // m[levels] == 1
+        size_t scratch = 0;
+        for (int l = 0; l < levels; l++) scratch += m[l] + m[l + 1];  // running products + totals
+        int rc = c.ensure_workspace((scratch + 1) * sizeof(Fe));
+        if (rc) return rc;
+        uint4* base = (uint4*)c.ws;
+        std::vector<uint4*> pre(levels), tot(levels + 1);
+        size_t off = 0;
+        for (int l = 0; l < levels; l++) {
+            pre[l] = base + 2 * off;
+            off += m[l];
+            tot[l] = base + 2 * off;
+            off += m[l + 1];
+        }
+        auto input = [&](int l) -> uint4* { return l == 0 ? a : tot[l - 1]; };
+        for (int l = 0; l < levels; l++) {
+            const size_t M = m[l + 1];
+            ProfScope ps(c, st, "batch_inv_up");
+            binv_up_kernel<F><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(input(l), pre[l], tot[l], m[l], M, 0u);
+        }
+        {
+            ProfScope ps(c, st, "batch_inv_top");
+            binv_top_kernel<F><<<1, 32, 0, st>>>(input(levels), d_status, 0u);
+        }
+        for (int l = levels - 1; l >= 0; l--) {
+            const size_t M = m[l + 1];
+            ProfScope ps(c, st, "batch_inv_down");
+            binv_down_kernel<F><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(input(l), pre[l], tot[l], input(l), m[l], M,
+                                                                             d_status, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
+    // d_out[0] <- sum_j a[j] * g^j
+    static int evaluate_at(Ctx& c, const uint4* a, size_t n, const Fe& g, uint4* d_out, cudaStream_t st) {
+        Fld f;
+        if (n == 0) {
+            HODOR_CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(Fe), st));
+            return HODOR_OK;
+        }
+        const uint32_t K = n >= ((size_t)1 << 22) ? 128u : (n >= ((size_t)1 << 16) ? 32u : 8u);
+        const size_t M = (n + K - 1) / K;
+        const unsigned blocks = (unsigned)((M + 255) / 256);
+        int rc = c.ensure_workspace((size_t)blocks * sizeof(Fe));
+        if (rc) return rc;
+        FePre gM;
+        f.make_pre(f.pow(g, (uint64_t)M), gM.w, gM.q);
+        {
+            ProfScope ps(c, st, "evaluate_at");
+            eval_partial_kernel<F><<<blocks, 256, 0, st>>>(a, n, M, K, g, gM, (uint4*)c.ws, 0u);
+        }
+        {
+            ProfScope ps(c, st, "evaluate_at_final");
+            eval_final_kernel<F><<<1, 256, 0, st>>>((const uint4*)c.ws, blocks, d_out, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
     // ------------------------------------------------------------------ Merkle tail, FRI fold
     static int merkle_tail(Ctx& c, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
                            cudaStream_t st) {
@@ -605,6 +677,8 @@ struct Ops {
         o.ntt = ntt;
         o.scale_pow = scale_pow;
         o.elementwise = elementwise;
+        o.batch_inversion = batch_inversion;
+        o.evaluate_at = evaluate_at;
         o.merkle_tail = merkle_tail;
         o.fri_fold = fri_fold;
         o.shard_rows = shard_rows;
@@ -648,7 +722,7 @@ int Ops<F>::shard_rows(Ctx& c, const uint4* in, uint4* out, uint32_t log_n, uint
         const Fe w16 = pow2k(omega, log_n - 4);
         Fe acc = w16;
         for (int k = 0; k < 7; k++) {
-            p.wr[k] = acc;
+            f.make_pre(acc, p.wr[k].w, p.wr[k].q);
             acc = f.mul(acc, w16);
         }
     }

@@ -33,6 +33,12 @@ enum : uint32_t {
     PASS_OUT_POW = 2u,    // last pass: multiply output k by out_pow^k (icoset_fft: g^-k, n^-1 folded into lo)
 };
 
+// A fixed multiplier in the form Field<F>::mul_pre wants: w = plain value, q = floor(w * 2^256 / p).
+// Tables of these are 64 bytes per entry (w then q).
+struct FePre {
+    Fe w, q;
+};
+
 struct NttPass {
     const uint4* in;
     uint4* out;
@@ -47,18 +53,20 @@ struct NttPass {
     uint32_t zero;      // always 0; opaque to ptxas (keeps the modulus in vector registers)
     uint32_t coset_stride_lo, coset_stride_hi;  // elements between per-coset tables
     TwoLevel tw;        // powers of omega
-    const uint4* tw_b;  // omega_B^x, x in [0, 2^B)
-    const uint4* tw_direct;  // inter-pass twiddles omega_N^x, x in [0, N = 2^(s+B)), when N <= 2^16; else null
+    // Tables read directly as multipliers are in FePre form (64 B per entry); the two-level tables,
+    // whose entries are multiplied with each other first, stay in Montgomery form.
+    const uint4* tw_b;  // omega_B^x, x in [0, 2^B)  (FePre)
+    const uint4* tw_direct;  // inter-pass twiddles omega_N^x, x in [0, N = 2^(s+B)), when N <= 2^16; else null  (FePre)
     // Expanded tables (the GPU counterpart of the reference's PrecomputedOmegas, src/precomputations/
     // mod.rs:14-66), streamed with the same coalesced addressing as the data; null => multiply two
     // table entries instead.  tw_full[(k << s) + r] = omega^(k * r) for pass 1 (n entries);
-    // coset_full[i * n + j] = shift_i^j (L * n entries).
+    // coset_full[i * n + j] = shift_i^j (L * n entries).  Both FePre.
     const uint4* tw_full;
     const uint4* coset_full;
     TwoLevel coset;     // pass 1 of a scaled transform: shift_i^j tables, coset i at +i*coset_stride
     TwoLevel out_pow;   // PASS_OUT_POW
-    Fe out_const;       // PASS_OUT_CONST
-    Fe wr[7];           // omega_16^k, k = 1..7  (omega_8 = wr[1], omega_4 = wr[3])
+    FePre out_const;    // PASS_OUT_CONST
+    FePre wr[7];        // omega_16^k, k = 1..7  (omega_8 = wr[1], omega_4 = wr[3])
 };
 
 DEV Fe ld_fe(const uint4* base, size_t idx) {
@@ -71,6 +79,25 @@ DEV Fe ld_fe(const uint4* base, size_t idx) {
 DEV void st_fe(uint4* base, size_t idx, const Fe& r) {
     base[2 * idx] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
     base[2 * idx + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+DEV FePre ld_pre(const uint4* base, size_t idx) {
+    const uint4 a = base[4 * idx], b = base[4 * idx + 1], c = base[4 * idx + 2], d = base[4 * idx + 3];
+    FePre r;
+    r.w.v[0] = a.x; r.w.v[1] = a.y; r.w.v[2] = a.z; r.w.v[3] = a.w;
+    r.w.v[4] = b.x; r.w.v[5] = b.y; r.w.v[6] = b.z; r.w.v[7] = b.w;
+    r.q.v[0] = c.x; r.q.v[1] = c.y; r.q.v[2] = c.z; r.q.v[3] = c.w;
+    r.q.v[4] = d.x; r.q.v[5] = d.y; r.q.v[6] = d.z; r.q.v[7] = d.w;
+    return r;
+}
+DEV void st_pre(uint4* base, size_t idx, const FePre& r) {
+    base[4 * idx] = make_uint4(r.w.v[0], r.w.v[1], r.w.v[2], r.w.v[3]);
+    base[4 * idx + 1] = make_uint4(r.w.v[4], r.w.v[5], r.w.v[6], r.w.v[7]);
+    base[4 * idx + 2] = make_uint4(r.q.v[0], r.q.v[1], r.q.v[2], r.q.v[3]);
+    base[4 * idx + 3] = make_uint4(r.q.v[4], r.q.v[5], r.q.v[6], r.q.v[7]);
+}
+template <class F>
+DEV Fe mul_by(const Field<F>& fld, const Fe& a, const FePre& m) {
+    return fld.mul_pre(a, m.w, m.q);
 }
 // shared-memory tile: two planes of uint4 so that a quarter warp touching 8 adjacent columns
 // reads 128 contiguous bytes
@@ -91,6 +118,12 @@ DEV Fe ld_param(const Fe& c, uint32_t opaque_zero) {
     Fe r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = c.v[i] | (HODOR_MODULUS_IN_REGS ? opaque_zero : 0u);
+    return r;
+}
+DEV FePre ld_param(const FePre& c, uint32_t opaque_zero) {
+    FePre r;
+    r.w = ld_param(c.w, opaque_zero);
+    r.q = ld_param(c.q, opaque_zero);
     return r;
 }
 
@@ -125,7 +158,7 @@ DEV void dif_inreg(const Field<F>& fld, Fe (&x)[1 << LOGR], const NttPass& p, ui
                 if (e == 0) {
                     x[blk + i + half] = d;
                 } else {
-                    x[blk + i + half] = fld.mul(d, ld_param(p.wr[e - 1], opaque_zero));
+                    x[blk + i + half] = mul_by(fld, d, ld_param(p.wr[e - 1], opaque_zero));
                 }
             }
         }
@@ -169,7 +202,7 @@ DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t ti
             Fe v = x[bitrev_c(k, LOGR)];
             const uint32_t pos = base + ((uint32_t)k << SL);
             if constexpr (SL > 0) {
-                if (k > 0) v = fld.mul(v, ld_fe(p.tw_b, (size_t)((k * lo) << TWSH)));
+                if (k > 0) v = mul_by(fld, v, ld_pre(p.tw_b, (size_t)((k * lo) << TWSH)));
             }
             if constexpr (TO_GLOBAL) store_global(pos, c, v);
             else sts_fe(sm, PLANE, pos * 8 + c, v);
@@ -243,11 +276,11 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
             Fe v = ld_fe(p.in, idx);
             if constexpr (SCALE_IN) {
                 // j = idx (u == 0 in pass 1): a[j] * shift_i^j
-                Fe w;
-                if (p.coset_full != nullptr) w = ld_fe(p.coset_full, (size_t)coset_hi * n + idx);
-                else w = two_level_pow(fld, p.coset, (size_t)coset_hi * p.coset_stride_lo,
-                                       (size_t)coset_hi * p.coset_stride_hi, idx);
-                v = fld.mul(v, w);
+                if (p.coset_full != nullptr)
+                    v = mul_by(fld, v, ld_pre(p.coset_full, (size_t)coset_hi * n + idx));
+                else
+                    v = fld.mul(v, two_level_pow(fld, p.coset, (size_t)coset_hi * p.coset_stride_lo,
+                                                 (size_t)coset_hi * p.coset_stride_hi, idx));
             }
             return v;
         } else {
@@ -264,11 +297,9 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
             // omega_N^(kloc * r): one lookup when the sub-transform is short enough for a flat table
             // (2 MiB at N = 2^16, L2 resident), else hi * lo from the two-level tables (one more multiply)
             const uint64_t prod = (uint64_t)kloc * (col0 + c);
-            Fe w;
-            if (p.tw_full != nullptr) w = ld_fe(p.tw_full, ((size_t)kloc << p.s) + col0 + c);
-            else if (p.tw_direct != nullptr) w = ld_fe(p.tw_direct, (size_t)prod);
-            else w = two_level_pow(fld, p.tw, 0, 0, prod << p.tw_shift);
-            v = fld.mul(v, w);
+            if (p.tw_full != nullptr) v = mul_by(fld, v, ld_pre(p.tw_full, ((size_t)kloc << p.s) + col0 + c));
+            else if (p.tw_direct != nullptr) v = mul_by(fld, v, ld_pre(p.tw_direct, (size_t)prod));
+            else v = fld.mul(v, two_level_pow(fld, p.tw, 0, 0, prod << p.tw_shift));
             st_fe(p.out, out_base + ((size_t)kloc << p.s) + c, v);
         } else {
             const uint32_t i = (coset_hi << li) | (c & ((1u << li) - 1u));
@@ -277,7 +308,7 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
             uint32_t midrev = mid;
             if (p.mid1) midrev = (mid >> p.mid1) | ((mid & ((1u << p.mid1) - 1u)) << p.mid0);
             const size_t k = (size_t)k1 | ((size_t)midrev << p.b1) | ((size_t)kloc << (ln - B));
-            if (p.flags & PASS_OUT_CONST) v = fld.mul(v, ld_param(p.out_const, oz));
+            if (p.flags & PASS_OUT_CONST) v = mul_by(fld, v, ld_param(p.out_const, oz));
             if (p.flags & PASS_OUT_POW) v = fld.mul(v, two_level_pow(fld, p.out_pow, 0, 0, k));
             st_fe(p.out, (size_t)i + (k << p.log_l), v);
         }
@@ -349,19 +380,26 @@ __global__ void __launch_bounds__(1024) ntt_small_kernel(const __grid_constant__
 // Tables and elementwise helpers
 // ------------------------------------------------------------------------------------------------
 // out[b * count + i] = bases[b]^i * (scale ? scale[0] : 1)
-template <class F>
+// PRE: entries in FePre form (64 B) for tables that are read directly as multipliers
+template <class F, bool PRE = false>
 __global__ void pow_table_kernel(uint4* out, const Fe* bases, const Fe* scale, uint32_t count, uint32_t zero) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const Field<F> fld(threadIdx.x & zero);
     Fe r = fld.pow(bases[blockIdx.y], i);
     if (scale != nullptr) r = fld.mul(r, scale[0]);
-    st_fe(out, (size_t)blockIdx.y * count + i, r);
+    if constexpr (PRE) {
+        FePre m;
+        fld.make_pre(r, m.w, m.q);
+        st_pre(out, (size_t)blockIdx.y * count + i, m);
+    } else {
+        st_fe(out, (size_t)blockIdx.y * count + i, r);
+    }
 }
 
 // Expanded tables.  out[b * n + j] = bases_b^j  (coset scaling for every coset b), or with
 // `boundary_s` >= 0: out[idx] = omega^((idx >> s) * (idx & (2^s - 1))), the pass-1 inter-pass twiddle
-// stored at the address of the element it multiplies.
+// stored at the address of the element it multiplies.  Entries are FePre (64 B).
 template <class F>
 __global__ void expand_table_kernel(uint4* out, TwoLevel t, uint32_t stride_lo, uint32_t stride_hi, size_t n,
                                     int boundary_s, uint32_t zero) {
@@ -370,7 +408,9 @@ __global__ void expand_table_kernel(uint4* out, TwoLevel t, uint32_t stride_lo, 
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
         uint64_t e = j;
         if (boundary_s >= 0) e = (uint64_t)(j >> boundary_s) * (j & (((size_t)1 << boundary_s) - 1));
-        st_fe(out, b * n + j, two_level_pow(fld, t, b * stride_lo, b * stride_hi, e));
+        FePre m;
+        fld.make_pre(two_level_pow(fld, t, b * stride_lo, b * stride_hi, e), m.w, m.q);
+        st_pre(out, b * n + j, m);
     }
 }
 

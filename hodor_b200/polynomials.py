@@ -179,3 +179,18 @@ class Polynomial:
 
     def scale(self, worker: Optional[Worker], g) -> None:
         self._ew(3, fld.limbs(g).reshape(1, 4))
+
+    # ---- batch inversion (:889-954) and point evaluation (:685-711) ------------------------------
+    def batch_inversion(self, worker: Optional[Worker] = None) -> None:
+        """Every value replaced by its inverse; SynthesisError (vector untouched) if one is zero."""
+        self._need(VALUES)
+        ensure_init()
+        check(lib.hodor_cuda_batch_inversion(_p(self.coeffs), C.c_uint64(self.size()), self.field_id))
+
+    def evaluate_at(self, worker: Optional[Worker], g) -> np.ndarray:
+        """sum_j coeffs[j] * g^j as 4 Montgomery limbs."""
+        self._need(COEFFICIENTS)
+        ensure_init()
+        out = np.zeros(4, np.uint64)
+        check(lib.hodor_cuda_evaluate_at(_p(self.coeffs), C.c_uint64(self.size()), _p(fld.limbs(g)), _p(out), self.field_id))
+        return out

@@ -44,6 +44,7 @@ extern "C" {
 #define HODOR_ERR_CUDA (-3)         /* no device, launch or runtime failure */
 #define HODOR_ERR_OOM (-4)
 #define HODOR_ERR_NOT_A_ROOT (-5)   /* omega is not a primitive 2^log_n-th root of unity */
+#define HODOR_ERR_NOT_INVERTIBLE (-6) /* batch_inversion met a zero: reference returns Err(SynthesisError::Error), src/polynomials/mod.rs:919 */
 
 /* ---- context ------------------------------------------------------------------------------ */
 int hodor_cuda_device_count(void);
@@ -104,6 +105,13 @@ int hodor_cuda_lde(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, 
  * 3 scale (b is one element).  out may alias a. */
 int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id);
 
+/* Polynomial<F, Values>::batch_inversion (src/polynomials/mod.rs:889-954): a[i] <- a[i]^-1 in place.
+ * A zero element fails with HODOR_ERR_NOT_INVERTIBLE and leaves `a` untouched, like the reference,
+ * which returns Err(SynthesisError::Error) before writing anything. */
+int hodor_cuda_batch_inversion(uint64_t* a, uint64_t n, int field_id);
+/* Polynomial<F, Coefficients>::evaluate_at (src/polynomials/mod.rs:685-711): out = sum_j coeffs[j] * g^j */
+int hodor_cuda_evaluate_at(const uint64_t* coeffs, uint64_t n, const uint64_t g[4], uint64_t out[4], int field_id);
+
 /* ---- Merkle oracle, host memory ----------------------------------------------------------- */
 /* Blake2sIopTree::create (src/iop/blake2s_trivial_iop.rs:131-219).  n a power of two >= 2;
  * nodes receives n * 32 bytes. */
@@ -151,6 +159,11 @@ int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes,
 int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
                             const void* d_challenge, void* d_out, int field_id, void* stream);
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
+                               void* stream);
+/* d_status: one device int, set to 0 on success and to 1 (vector untouched) when an element is zero */
+int hodor_cuda_batch_inversion_dev(void* d_a, uint64_t n, int* d_status, int field_id, void* stream);
+/* d_out: one element (32 B) on the device */
+int hodor_cuda_evaluate_at_dev(const void* d_coeffs, uint64_t n, const uint64_t g[4], void* d_out, int field_id,
                                void* stream);
 /* Building blocks for an LDE + FRI commit sharded over G = 2^log_g GPUs (hodor_b200/sharded.py):
  * - the cosets i = first_coset + coset_stride * t (t < 2^log_count) of the L = 2^log_factor coset LDE,

@@ -2,6 +2,7 @@
 // 256-bit Montgomery multiplications per second and Blake2s compressions per second on one B200.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o build/microbench tools/microbench.cu
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include "../hodor_b200/csrc/field.cuh"
 #include "../hodor_b200/csrc/merkle.cuh"
@@ -24,6 +25,36 @@ __global__ void __launch_bounds__(256) mul_kernel(const Fe* in, Fe* out, int ite
 #pragma unroll
     for (int j = 1; j < ILP; j++) acc = fld.add(acc, x[j]);
     out[tid] = acc;
+}
+
+// fixed-operand multiplier (Field::mul_pre): x <- x * w with (w, wq) precomputed
+template <class F, int ILP, uint32_t GUARD>
+__global__ void __launch_bounds__(256) mul_pre_kernel(const Fe* in, Fe* out, int iters, uint32_t zero) {
+    const Field<F> fld(0u);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Fe x[ILP];
+    Fe w, wq;
+    fld.make_pre(in[(tid + 1) & 1023], w, wq);
+#pragma unroll
+    for (int j = 0; j < ILP; j++) x[j] = in[(tid + 7 * j) & 1023];
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) x[j] = fld.template mul_pre<GUARD>(x[j], w, wq);
+    }
+    Fe acc = x[0];
+#pragma unroll
+    for (int j = 1; j < ILP; j++) acc = fld.add(acc, x[j]);
+    out[tid] = acc;
+}
+// same chain through the Montgomery multiplier: must give identical bits
+template <class F>
+__global__ void __launch_bounds__(256) mul_ref_kernel(const Fe* in, Fe* out, int iters, uint32_t zero) {
+    const Field<F> fld(0u);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Fe x = in[tid & 1023];
+    const Fe y = in[(tid + 1) & 1023];
+    for (int k = 0; k < iters; k++) x = fld.mul_evenodd(x, y);
+    out[tid] = x;
 }
 
 template <class F>
@@ -87,6 +118,23 @@ int main() {
     cudaMalloc(&d_out, sizeof(Fe) * sms * 16 * 256);
     cudaMemcpy(d_in, h.data(), sizeof(Fe) * 1024, cudaMemcpyHostToDevice);
     const int iters = 2000;
+    {   // parity of mul_pre (normal guard, and guard forced low so the out-of-line fix-up runs half the time)
+        const int nthr = sms * 256;
+        std::vector<Fe> r0(nthr), r1(nthr), r2(nthr);
+        mul_ref_kernel<BlsFr><<<sms, 256>>>(d_in, d_out, 300, 0u);
+        cudaMemcpy(r0.data(), d_out, sizeof(Fe) * nthr, cudaMemcpyDeviceToHost);
+        mul_pre_kernel<BlsFr, 1, 0xfffffff2u><<<sms, 256>>>(d_in, d_out, 300, 0u);
+        cudaMemcpy(r1.data(), d_out, sizeof(Fe) * nthr, cudaMemcpyDeviceToHost);
+        mul_pre_kernel<BlsFr, 1, 0x80000000u><<<sms, 256>>>(d_in, d_out, 300, 0u);
+        cudaMemcpy(r2.data(), d_out, sizeof(Fe) * nthr, cudaMemcpyDeviceToHost);
+        int bad1 = 0, bad2 = 0;
+        for (int i = 0; i < nthr; i++) {
+            bad1 += memcmp(&r0[i], &r1[i], sizeof(Fe)) != 0;
+            bad2 += memcmp(&r0[i], &r2[i], sizeof(Fe)) != 0;
+        }
+        printf("{\"check\": \"mul_pre_vs_mont\", \"threads\": %d, \"chain\": 300, \"mismatch\": %d, \"mismatch_forced_fixup\": %d, \"err\": \"%s\"}\n",
+               nthr, bad1, bad2, cudaGetErrorString(cudaGetLastError()));
+    }
     for (int bps : {1, 2, 4, 8}) {
         dim3 grid(sms * bps), block(256);
         const double threads = (double)sms * bps * 256;
@@ -97,6 +145,16 @@ int main() {
                ILP, (int)REGS, bps, threads * iters * ILP / ms / 1e6);                                      \
     }
         RUN_MUL(BlsFr, 1, false, "mont_mul_bls")
+#define RUN_PRE(F, ILP, NAME)                                                                                 \
+    {                                                                                                        \
+        double ms = time_ms(mul_pre_kernel<F, ILP, 0xfffffff2u>, grid, block, (const Fe*)d_in, d_out, iters, 0u); \
+        printf("{\"bench\": \"%s\", \"ilp\": %d, \"blocks_per_sm\": %d, \"gmul_per_s\": %.2f}\n", NAME, ILP, bps, \
+               threads * iters * ILP / ms / 1e6);                                                            \
+    }
+        RUN_PRE(BlsFr, 1, "mul_pre_bls")
+        RUN_PRE(BlsFr, 2, "mul_pre_bls")
+        RUN_PRE(Bn254Fr, 1, "mul_pre_bn254")
+        RUN_PRE(Stark252, 1, "mul_pre_stark")
         {
             double ms = time_ms(mul_kernel<BlsFr, 1, false, true>, grid, block, (const Fe*)d_in, d_out, iters, 0u);
             printf("{\"bench\": \"mont_mul_bls_split\", \"blocks_per_sm\": %d, \"gmul_per_s\": %.2f}\n", bps, threads * iters / ms / 1e6);
