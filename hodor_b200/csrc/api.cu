@@ -637,6 +637,17 @@ int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_
     HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return HODOR_OK;
 }
+int hodor_cuda_selftest_mul_pre(int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    unsigned long long* d = (unsigned long long*)(c->small + 70);
+    int rc = ops->selftest_mul_pre(*c, d, c->stream);
+    if (rc) return rc;
+    unsigned long long bad = 0;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(&bad, d, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return bad > 0x7fffffffull ? 0x7fffffff : (int)bad;
+}
 int hodor_cuda_batch_inversion(uint64_t* a, uint64_t n, int field_id) {
     LOCKED_CTX();
     GET_OPS(field_id);

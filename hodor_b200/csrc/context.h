@@ -79,7 +79,7 @@ struct Ctx {
     // expanded (one entry per element) twiddle / coset-power tables; bounded by full_budget bytes
     std::map<std::string, std::pair<uint4*, size_t>> full_tables;
     size_t full_bytes = 0;
-    size_t full_budget = (size_t)12 << 30;  // HODOR_TABLE_BUDGET_MB overrides; 0 disables
+    size_t full_budget = (size_t)24 << 30;  // HODOR_TABLE_BUDGET_MB overrides; 0 disables
 
     std::vector<std::pair<void*, size_t>> pool_free_list;
     std::map<void*, size_t> pool_live;
@@ -147,6 +147,7 @@ struct FieldOps {
     int (*elementwise)(Ctx&, int op, const uint4* a, const uint4* b, uint4* out, size_t n, cudaStream_t st);
     int (*batch_inversion)(Ctx&, uint4* a, size_t n, int* d_status, cudaStream_t st);
     int (*evaluate_at)(Ctx&, const uint4* a, size_t n, const Fe& g, uint4* d_out, cudaStream_t st);
+    int (*selftest_mul_pre)(Ctx&, unsigned long long* d_mismatch, cudaStream_t st);
     int (*merkle_tail)(Ctx&, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
                        cudaStream_t st);
     int (*fri_fold)(Ctx&, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,

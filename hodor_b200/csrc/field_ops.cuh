@@ -471,20 +471,23 @@ struct Ops {
             // make room once, before any pointer is handed out: drop every expanded table if this
             // call's tables would not fit beside the cached ones
             const std::string bkey = key_of("bfull", log_n, s0, &omega, 1);
-            const size_t want = (c.full_tables.count(bkey) ? 0 : n * sizeof(FePre)) + (coset ? n * L * sizeof(FePre) : 0);
+            std::string ckey;
+            if (coset) {
+                std::vector<Fe> kb{*shift0};
+                if (step) kb.push_back(*step);
+                ckey = key_of("cfull", log_n, log_l, kb.data(), (int)kb.size());
+            }
+            const size_t want = (c.full_tables.count(bkey) ? 0 : n * sizeof(FePre)) +
+                                (coset && !c.full_tables.count(ckey) ? n * L * sizeof(FePre) : 0);
             if (c.full_bytes + want > c.full_budget && !c.full_tables.empty()) {
                 cudaDeviceSynchronize();
                 for (auto& kv : c.full_tables) cudaFree(kv.second.first);
                 c.full_tables.clear();
                 c.full_bytes = 0;
             }
-            tw_full = get_full_table(c, key_of("bfull", log_n, s0, &omega, 1), tw->pw.two_level(), 0, 0, n, 1, (int)s0, st);
-            if (coset) {
-                std::vector<Fe> kb{*shift0};
-                if (step) kb.push_back(*step);
-                coset_full = get_full_table(c, key_of("cfull", log_n, log_l, kb.data(), (int)kb.size()), coset->two_level(),
-                                            coset->stride_lo(), coset->stride_hi(), n, L, -1, st);
-            }
+            tw_full = get_full_table(c, bkey, tw->pw.two_level(), 0, 0, n, 1, (int)s0, st);
+            if (coset)
+                coset_full = get_full_table(c, ckey, coset->two_level(), coset->stride_lo(), coset->stride_hi(), n, L, -1, st);
         }
         p.coset_full = coset_full;
         uint32_t below = log_n;
@@ -590,6 +593,14 @@ struct Ops {
         return HODOR_OK;
     }
 
+    static int selftest_mul_pre(Ctx& c, unsigned long long* d_mismatch, cudaStream_t st) {
+        HODOR_CUDA_TRY(cudaMemsetAsync(d_mismatch, 0, sizeof(unsigned long long), st));
+        ProfScope ps(c, st, "selftest_mul_pre");
+        selftest_mul_pre_kernel<F><<<148 * 2, 256, 0, st>>>(d_mismatch, 0u);
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
     // d_out[0] <- sum_j a[j] * g^j
     static int evaluate_at(Ctx& c, const uint4* a, size_t n, const Fe& g, uint4* d_out, cudaStream_t st) {
         Fld f;
@@ -679,6 +690,7 @@ struct Ops {
         o.elementwise = elementwise;
         o.batch_inversion = batch_inversion;
         o.evaluate_at = evaluate_at;
+        o.selftest_mul_pre = selftest_mul_pre;
         o.merkle_tail = merkle_tail;
         o.fri_fold = fri_fold;
         o.shard_rows = shard_rows;

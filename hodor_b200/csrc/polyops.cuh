@@ -50,7 +50,13 @@ __global__ void binv_top_kernel(uint4* x, int* status, uint32_t zero) {
     uint32_t e[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) e[i] = F::P(i);
-    e[0] -= 2u;  // p is odd and > 2: no borrow
+    uint32_t borrow = 2u;  // e = p - 2
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t old = e[i];
+        e[i] = old - borrow;
+        borrow = old < borrow ? 1u : 0u;
+    }
     Fe acc = Field<F>::one();
     for (int i = 255; i >= 0; i--) {
         acc = fld.mul(acc, acc);
@@ -122,6 +128,37 @@ __global__ void __launch_bounds__(256) eval_final_kernel(const uint4* partial, s
         __syncthreads();
     }
     if (threadIdx.x == 0) st_fe(out, 0, ld_fe(sm, 0));
+}
+
+// Self-test of Field::mul_pre: a chain of multiplications through the Montgomery multiplier, through
+// mul_pre, and through mul_pre with the guard threshold forced down to 2^31 (so the out-of-line
+// carry fix-up runs on about half of all multiplies); *mismatch counts threads that disagree.
+template <class F>
+__global__ void __launch_bounds__(256) selftest_mul_pre_kernel(unsigned long long* mismatch, uint32_t zero) {
+    const uint32_t oz = threadIdx.x & zero;
+    const Field<F> fld(oz);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Fe g = Field<F>::zero();
+    g.v[0] = F::GENERATOR;
+    g = fld.to_mont(g);
+    Fe x = fld.pow(g, 0x9e3779b9ull * (tid + 1));
+    Fe w = fld.pow(g, 0x85ebca6bull * (tid + 3));
+    if (tid == 0) w = fld.neg(Field<F>::one());  // p - 1 in Montgomery form
+    if (tid == 1) w = Field<F>::one();
+    if (tid == 2) x = Field<F>::zero();
+    FePre m;
+    fld.make_pre(w, m.w, m.q);
+    Fe r1 = x, r2 = x, r3 = x;
+    bool bad = false;
+    for (int i = 0; i < 48; i++) {
+        r1 = fld.mul(r1, w);
+        r2 = fld.mul_pre(r2, m.w, m.q);
+        r3 = fld.template mul_pre<0x80000000u>(r3, m.w, m.q);
+        bad |= !Field<F>::eq(r1, r2) || !Field<F>::eq(r1, r3) || !fld.is_canonical(r2);
+        w = fld.add(w, r1);  // a fresh multiplier every step
+        fld.make_pre(w, m.w, m.q);
+    }
+    if (bad) atomicAdd(mismatch, 1ull);
 }
 
 }  // namespace hodor

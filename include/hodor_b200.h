@@ -185,6 +185,10 @@ int hodor_cuda_ntt_shard_cols_dev(const void* d_in, void* d_out, uint32_t log_n,
 int hodor_cuda_ntt_shard_rows_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
                                   const uint64_t omega[4], int field_id, void* stream);
 
+/* Diagnostic: runs the fixed-operand multiplier behind every table multiply (Field::mul_pre)
+ * against the Montgomery multiplier on the device, with its rare carry fix-up path forced on.
+ * Returns the number of disagreeing threads (0 = pass). */
+int hodor_cuda_selftest_mul_pre(int field_id);
 /* kernels launched by this library since init (bench.py's gpu_launches) */
 uint64_t hodor_cuda_launch_count(void);
 /* Optional per-kernel timing: between begin and end every launch is bracketed by CUDA events on

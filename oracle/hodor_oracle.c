@@ -704,6 +704,84 @@ API int oracle_fri_commit(int field, const uint64_t *lde, size_t n, uint32_t lde
     return num_steps;
 }
 
+/* ------------------------------------------------------------------ Polynomial::evaluate_at (src/polynomials/mod.rs:685-711) */
+/* Worker::get_num_spawned_threads (src/fft/multicore.rs:87-102) */
+static size_t num_spawned_threads(size_t elements, size_t cpus) {
+    if (elements < cpus) return elements;
+    size_t chunk = chunk_size(elements, cpus), n = elements / chunk;
+    if (elements % chunk != 0) n++;
+    return n;
+}
+typedef struct { const field_t *F; const fe *a; size_t n, chunk; fe g; fe *sub; } ev_t;
+static void ev_job(void *p, size_t i) {
+    ev_t *d = (ev_t *)p; const field_t *F = d->F;
+    size_t b = i * d->chunk, e = b + d->chunk; if (e > d->n) e = d->n;
+    fe x; fe_pow_u64(F, &x, &d->g, (uint64_t)(i * d->chunk));          /* :695 */
+    fe s; memset(&s, 0, sizeof s);
+    for (size_t k = b; k < e; k++) {                                    /* :696-701 */
+        fe v; fe_mul(F, &v, &x, &d->a[k]); fe_add(F, &s, &s, &v); fe_mul(F, &x, &x, &d->g);
+    }
+    d->sub[i] = s;
+}
+API int oracle_evaluate_at(int field, const uint64_t *coeffs, size_t n, const uint64_t *g, uint32_t cpus, uint64_t *out) {
+    const field_t *F = get_field(field); if (!F || cpus == 0) return -1;
+    fe res; memset(&res, 0, sizeof res);
+    if (n) {
+        size_t threads = num_spawned_threads(n, cpus);
+        ev_t d; d.F = F; d.a = (const fe *)coeffs; d.n = n; d.chunk = chunk_size(n, cpus); d.g = *(const fe *)g;
+        d.sub = (fe *)calloc(threads, sizeof(fe));
+        run_jobs(threads, ev_job, &d);
+        for (size_t i = 0; i < threads; i++) fe_add(F, &res, &res, &d.sub[i]);   /* :706-709 */
+        free(d.sub);
+    }
+    memcpy(out, &res, 32);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ Polynomial::batch_inversion (src/polynomials/mod.rs:889-954) */
+typedef struct { const field_t *F; fe *a; fe *grand; fe *sub; size_t n, chunk; } bi_t;
+static void bi_up_job(void *p, size_t i) {                              /* :897-908 */
+    bi_t *d = (bi_t *)p; const field_t *F = d->F;
+    size_t b = i * d->chunk, e = b + d->chunk; if (e > d->n) e = d->n;
+    fe s = F->r;
+    for (size_t k = b; k < e; k++) { fe_mul(F, &s, &s, &d->a[k]); d->grand[k] = s; }
+    d->sub[i] = s;
+}
+static void bi_down_job(void *p, size_t i) {                            /* :934-951; sub[] now holds the sub-inverses */
+    bi_t *d = (bi_t *)p; const field_t *F = d->F;
+    size_t b = i * d->chunk, e = b + d->chunk; if (e > d->n) e = d->n;
+    fe s = d->sub[i];
+    for (size_t k = e; k-- > b;) {
+        fe tmp = d->a[k];
+        fe g = (k > b) ? d->grand[k - 1] : F->r;
+        fe_mul(F, &d->a[k], &g, &s);
+        fe_mul(F, &s, &s, &tmp);
+    }
+}
+/* returns 0, or -2 (vector untouched) when an element is zero: Err(SynthesisError::Error), :919 */
+API int oracle_batch_inversion(int field, uint64_t *a, size_t n, uint32_t cpus) {
+    const field_t *F = get_field(field); if (!F || cpus == 0) return -1;
+    if (n == 0) return 0;
+    size_t threads = num_spawned_threads(n, cpus);
+    bi_t d; d.F = F; d.a = (fe *)a; d.n = n; d.chunk = chunk_size(n, cpus);
+    d.grand = (fe *)malloc(n * sizeof(fe)); d.sub = (fe *)malloc(threads * sizeof(fe));
+    run_jobs(threads, bi_up_job, &d);
+    fe full = F->r, zero; memset(&zero, 0, sizeof zero);
+    for (size_t i = 0; i < threads; i++) fe_mul(F, &full, &full, &d.sub[i]);   /* :914-917 */
+    if (fe_eq(&full, &zero)) { free(d.grand); free(d.sub); return -2; }
+    fe pinv; fe_inv(F, &pinv, &full);
+    fe *subinv = (fe *)malloc(threads * sizeof(fe));
+    for (size_t i = 0; i < threads; i++) {                                      /* :922-932 */
+        fe t = pinv;
+        for (size_t j = 0; j < threads; j++) if (j != i) fe_mul(F, &t, &t, &d.sub[j]);
+        subinv[i] = t;
+    }
+    memcpy(d.sub, subinv, threads * sizeof(fe)); free(subinv);
+    run_jobs(threads, bi_down_job, &d);
+    free(d.grand); free(d.sub);
+    return 0;
+}
+
 /* SplitMix64 test-vector generator: limbs used directly as Montgomery form. */
 API int oracle_random_elements(int field, uint64_t *out, size_t count, uint64_t seed) {
     const field_t *F = get_field(field); if (!F) return -1;

@@ -195,6 +195,27 @@ def ifft(field, a, log_n, cpus=None, coset=False):
     return a
 
 
+def evaluate_at(field, coeffs, g, cpus=None) -> np.ndarray:
+    """Polynomial::evaluate_at (src/polynomials/mod.rs:685-711)."""
+    coeffs = np.ascontiguousarray(coeffs, np.uint64).reshape(-1, 4)
+    out = np.zeros(4, np.uint64)
+    _check(lib().oracle_evaluate_at(field, _p64(coeffs), C.c_size_t(coeffs.shape[0]),
+                                    _p64(np.ascontiguousarray(g, np.uint64)), cpus or default_cpus(), _p64(out)),
+           "evaluate_at")
+    return out
+
+
+def batch_inversion(field, a, cpus=None):
+    """Polynomial::batch_inversion (src/polynomials/mod.rs:889-954); None when an element is zero
+    (the reference returns Err(SynthesisError::Error) and leaves the vector untouched)."""
+    a = np.array(a, np.uint64, copy=True).reshape(-1, 4)
+    rc = lib().oracle_batch_inversion(field, _p64(a), C.c_size_t(a.shape[0]), cpus or default_cpus())
+    if rc == -2:
+        return None
+    _check(rc, "batch_inversion")
+    return a
+
+
 def lde(field, coeffs, log_n, factor, coset, cpus=None):
     coeffs = np.ascontiguousarray(coeffs, np.uint64).reshape(-1, 4)
     assert coeffs.shape[0] == 1 << log_n

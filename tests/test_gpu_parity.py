@@ -47,6 +47,91 @@ def test_elementwise_field_ops(hodor, oracle, fid):
     assert np.array_equal(out, oracle.mul(fid, a, np.tile(b[0], (n, 1))))
 
 
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_fixed_operand_multiplier_selftest(hodor, fid):
+    """Field::mul_pre (the multiplier of every table multiply) against the Montgomery multiplier on
+    the device, including with the guard threshold forced low so that the out-of-line carry fix-up
+    (taken about 3 times in 10^9 multiplies in production) runs on half of all multiplies."""
+    from hodor_b200 import _ffi
+
+    assert _ffi.check(_ffi.lib.hodor_cuda_selftest_mul_pre(fid)) == 0
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_batch_inversion_matches_oracle(hodor, oracle, fid):
+    """Polynomial::batch_inversion (src/polynomials/mod.rs:889-954; reference test :959-985):
+    every tree shape of the kernel (K = 16 per level), ragged sizes included."""
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+
+    for n in (1, 2, 5, 16, 17, 255, 256, 257, 4097, 1 << 16, (1 << 18) + 3):
+        a = oracle.random_elements(fid, n, seed=900 + n % 97)
+        want = oracle.batch_inversion(fid, a)
+        got = a.copy()
+        _ffi.check(_ffi.lib.hodor_cuda_batch_inversion(_p(got), C.c_uint64(n), fid))
+        assert np.array_equal(got, want), f"n={n}"
+    # a zero anywhere: Err(SynthesisError::Error), vector untouched (:919)
+    a = oracle.random_elements(fid, 1000, seed=7)
+    a[613] = 0
+    got = a.copy()
+    assert _ffi.lib.hodor_cuda_batch_inversion(_p(got), C.c_uint64(1000), fid) == _ffi.ERR_NOT_INVERTIBLE
+    assert np.array_equal(got, a)
+    poly = hodor.Polynomial.from_values(fid, a)
+    with pytest.raises(_ffi.SynthesisError):
+        poly.batch_inversion(hodor.Worker())
+    assert oracle.batch_inversion(fid, a) is None
+    a[613] = a[0]
+    poly = hodor.Polynomial.from_values(fid, a[:512])
+    poly.batch_inversion(hodor.Worker())
+    assert np.array_equal(poly.as_ref(), oracle.batch_inversion(fid, a[:512]))
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_evaluate_at_matches_oracle(hodor, oracle, fid):
+    """Polynomial::evaluate_at (src/polynomials/mod.rs:685-711)."""
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+
+    z = oracle.random_elements(fid, 1, seed=31)[0]
+    for n in (1, 2, 7, 8, 9, 255, 256, 257, 2049, 1 << 16, (1 << 16) + 1, (1 << 20) + 5):
+        a = oracle.random_elements(fid, n, seed=300 + n % 89)
+        out = np.zeros(4, np.uint64)
+        _ffi.check(_ffi.lib.hodor_cuda_evaluate_at(_p(a), C.c_uint64(n), _p(z), _p(out), fid))
+        assert np.array_equal(out, oracle.evaluate_at(fid, a, z)), f"n={n}"
+    a = oracle.random_elements(fid, 1 << 12, seed=3)
+    poly = hodor.Polynomial.from_coeffs(fid, a)
+    assert np.array_equal(poly.evaluate_at(hodor.Worker(), z), oracle.evaluate_at(fid, a, z))
+    # a coset LDE value IS the polynomial evaluated at g * w^idx
+    lde = hodor.Polynomial.from_coeffs(fid, a).coset_lde(hodor.Worker(), 4)
+    w = oracle.domain_generator(fid, 14)
+    g = oracle.field_constants(fid)["generator"]
+    for idx in (0, 1, 5, (1 << 14) - 1):
+        x = oracle.mul(fid, g, oracle.pow_(fid, w, idx))[0]
+        assert np.array_equal(poly.evaluate_at(hodor.Worker(), x), lde.as_ref()[idx])
+
+
+def test_batch_inversion_2p24_properties(hodor, oracle):
+    """BASELINE-size check without a 2^24 CPU pass: a * a^-1 == 1 everywhere, and inverting twice
+    returns the input."""
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+
+    fid, n = 0, 1 << 24
+    a = oracle.random_elements(fid, n, seed=24)
+    inv = a.copy()
+    _ffi.check(_ffi.lib.hodor_cuda_batch_inversion(_p(inv), C.c_uint64(n), fid))
+    prod = np.zeros_like(a)
+    _ffi.check(_ffi.lib.hodor_cuda_elementwise(0, _p(a), _p(inv), _p(prod), C.c_uint64(n), fid))
+    assert np.array_equal(prod, np.tile(oracle.field_constants(fid)["r"], (n, 1)))
+    inv_once = inv[[0, 1, n // 2, n - 1]].copy()
+    _ffi.check(_ffi.lib.hodor_cuda_batch_inversion(_p(inv), C.c_uint64(n), fid))
+    assert np.array_equal(inv, a)
+    idx = range(4)
+    a = a[[0, 1, n // 2, n - 1]]
+    for i in idx:
+        assert np.array_equal(inv_once[i], oracle.inverse(fid, a[i]))
+
+
 # ----------------------------------------------------------------------------------------------
 # NTT
 # ----------------------------------------------------------------------------------------------

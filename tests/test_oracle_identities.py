@@ -135,3 +135,25 @@ def test_fri_on_values_vs_on_coefficients(oracle, pymodel, fid):
     for i in range(len(pc.layer_values)):
         assert plain(F, pv.layer_values[i], oracle) == pc.layer_values[i]
         assert [x.tobytes() for x in pv.layer_nodes[i]] == pc.layer_nodes[i]
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_batch_inversion_and_evaluate_at(oracle, pymodel, fid):
+    """test_batch_inversion (src/polynomials/mod.rs:959-985): batch inverse == per-element inverse, for
+    every worker count; a zero element gives the reference's Err and leaves the vector alone.
+    evaluate_at (:685-711) == Horner on integers, for every worker count."""
+    F = getattr(pymodel, MODELS[fid])
+    a = oracle.random_elements(fid, 77, seed=5)
+    ai = plain(F, a, oracle)
+    want = [pow(x, -1, F.p) for x in ai]
+    for cpus in (1, 2, 3, 8, 200):
+        got = oracle.batch_inversion(fid, a, cpus=cpus)
+        assert plain(F, got, oracle) == want
+        for n in (0, 1, 5, 77):
+            z = a[3]
+            assert F.from_mont(oracle.limbs_to_int(oracle.evaluate_at(fid, a[:n], z, cpus=cpus))) == \
+                pymodel.evaluate(F, ai[:n], ai[3])
+    assert np.array_equal(oracle.batch_inversion(fid, a[:1])[0], oracle.inverse(fid, a[0]))
+    bad = a.copy()
+    bad[40] = 0
+    assert oracle.batch_inversion(fid, bad) is None
