@@ -41,7 +41,7 @@ struct CudaError : std::runtime_error {
 inline int check(int rc) {
     if (rc >= 0) return rc;
     const std::string msg = hodor_cuda_last_error();
-    if (rc == HODOR_ERR_DOMAIN) throw SynthesisError("General error for now: " + msg);
+    if (rc == HODOR_ERR_DOMAIN || rc == HODOR_ERR_NOT_INVERTIBLE) throw SynthesisError("General error for now: " + msg);
     if (rc == HODOR_ERR_INVALID_ARG) throw std::logic_error(msg);
     throw CudaError(msg);
 }
@@ -187,6 +187,16 @@ class Polynomial {
         require<Values>();
         check(hodor_cuda_ifft(raw(), exp, 1, F::ID));
         return Polynomial<F, Coefficients>::adopt(std::move(coeffs_));
+    }
+    void batch_inversion(const Worker&) {  // :889-954; SynthesisError (vector untouched) on a zero value
+        require<Values>();
+        check(hodor_cuda_batch_inversion(raw(), coeffs_.size(), F::ID));
+    }
+    F evaluate_at(const Worker&, const F& g) const {  // :685-711
+        require<Coefficients>();
+        F out;
+        check(hodor_cuda_evaluate_at(reinterpret_cast<const uint64_t*>(coeffs_.data()), coeffs_.size(), g.l, out.l, F::ID));
+        return out;
     }
     Polynomial clone() const { return Polynomial(coeffs_); }
 

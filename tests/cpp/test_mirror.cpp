@@ -14,6 +14,8 @@ int oracle_random_elements(int field, uint64_t* out, size_t count, uint64_t seed
 int oracle_serial_fft(int field, uint64_t* a, const uint64_t* omega, uint32_t log_n);
 int oracle_lde(int field, const uint64_t* coeffs, uint32_t log_n, uint32_t factor, int coset, uint64_t* out, uint32_t cpus);
 int oracle_merkle_create(int field, const uint64_t* leaves, size_t n, uint8_t* nodes, uint32_t cpus);
+int oracle_batch_inversion(int field, uint64_t* a, size_t n, uint32_t cpus);
+int oracle_evaluate_at(int field, const uint64_t* coeffs, size_t n, const uint64_t* g, uint32_t cpus, uint64_t* out);
 }
 
 static int failures = 0;
@@ -49,6 +51,40 @@ static void test_fft_roundtrip() {
         auto cback = Polynomial<F, Coefficients>::from_coeffs(a).coset_fft(worker).icoset_fft(worker);
         CHECK(cback.as_ref() == a);
     }
+}
+
+// test_batch_inversion (src/polynomials/mod.rs:959-985): batch inverse == per-element inverse;
+// evaluate_at (:685-711) against the oracle and against a coset LDE value
+template <class F>
+static void test_batch_inversion_and_evaluate() {
+    const Worker worker;
+    const auto a = random_vec<F>(1 << 10, 41);
+    auto values = Polynomial<F, Values>::from_values(a);
+    values.batch_inversion(worker);
+    for (size_t i = 0; i < a.size(); i += 97) CHECK(values.as_ref()[i] == a[i].inverse().second);
+    std::vector<F> want = a;
+    CHECK(oracle_batch_inversion(F::ID, reinterpret_cast<uint64_t*>(want.data()), want.size(), 4) == 0);
+    CHECK(values.as_ref() == want);
+    auto with_zero = a;
+    with_zero[77] = F::zero();
+    auto bad = Polynomial<F, Values>::from_values(with_zero);
+    bool threw = false;
+    try {
+        bad.batch_inversion(worker);
+    } catch (const SynthesisError&) {
+        threw = true;
+    }
+    CHECK(threw);
+    CHECK(bad.as_ref() == with_zero);
+    const auto coeffs = Polynomial<F, Coefficients>::from_coeffs(a);
+    const F z = a[5];
+    F expect;
+    oracle_evaluate_at(F::ID, reinterpret_cast<const uint64_t*>(a.data()), a.size(), z.l, 3, expect.l);
+    CHECK(coeffs.evaluate_at(worker, z) == expect);
+    const auto lde = coeffs.clone().coset_lde(worker, 4);
+    F x = F::multiplicative_generator();
+    x.mul_assign(Domain<F>::new_for_size(a.size() * 4).generator.pow(9));
+    CHECK(coeffs.evaluate_at(worker, x) == lde.as_ref()[9]);
 }
 
 // test_lde_correctness / test_coset_lde_correctness (src/polynomials/mod.rs:988, 1036)
@@ -183,6 +219,7 @@ static void run_all(const char* name) {
     test_domain<F>();
     test_fft_roundtrip<F>();
     test_lde_correctness<F>();
+    test_batch_inversion_and_evaluate<F>();
     test_small_iop<F>();
     test_one_fri_step<F>();
     std::printf("%s: %s\n", name, failures == before ? "ok" : "FAILED");

@@ -17,7 +17,7 @@ import os
 import sys
 
 IMM_FIRST = os.environ.get('IMM_FIRST', '1') == '1'
-IMM_ROLE = os.environ.get('IMM_ROLE', 'x')
+IMM_ROLE = os.environ.get('IMM_ROLE', 'y')
 SWAP_HI = os.environ.get('SWAP_HI', '0') == '1'
 
 
@@ -128,7 +128,10 @@ def gen_lo(xname, yfmt, imm, acc):
             if items:
                 body += chain(acc, par, items, yfmt.format(j=j), xname, imm)
         if imm and IMM_ROLE != 'x':
-            out.append(f"    if constexpr ({yfmt.format(j=j)} != 0u) {{\n{body}    }}\n")
+            # a word of NP equal to 2^32 - 1 is handled after the combine with two add/sub chains
+            # (ALU pipe) instead of 8 - j products; a zero word contributes nothing
+            y = yfmt.format(j=j)
+            out.append(f"    if constexpr ({y} != 0u && {y} != 0xffffffffu) {{\n{body}    }}\n")
         else:
             out.append(body)
     return "".join(out)
@@ -175,6 +178,32 @@ def main():
     w('        "addc.u32 %7, %15, %22;"\n')
     w("        : " + ", ".join(f'"=r"(r[{k}])' for k in range(8)) + "\n")
     w("        : " + ", ".join(f'"r"(e[{k}])' for k in range(8)) + ", " + ", ".join(f'"r"(o[{k}])' for k in range(1, 8)) + ");\n")
+    if IMM_ROLE != 'x':
+        for j in range(8):
+            # r += q * (2^32 - 1) * 2^(32 j)  =  r + (q << 32(j+1)) - (q << 32 j)   (mod 2^256)
+            w(f"    if constexpr (F::NP({j}) == 0xffffffffu) {{\n")
+            if j + 1 <= 7:
+                ks = list(range(j + 1, 8))
+                lines = []
+                for n, k in enumerate(ks):
+                    op = "add.cc.u32" if n == 0 else ("addc.cc.u32" if n < len(ks) - 1 else "addc.u32")
+                    if len(ks) == 1:
+                        op = "add.u32"
+                    lines.append(f"{op} %{n}, %{n}, %{len(ks) + n};")
+                w('        asm("' + '\\n\\t"\n            "'.join(lines) + '"\n')
+                w("            : " + ", ".join(f'"+r"(r[{k}])' for k in ks) + "\n")
+                w("            : " + ", ".join(f'"r"(q[{k - j - 1}])' for k in ks) + ");\n")
+            ks = list(range(j, 8))
+            lines = []
+            for n, k in enumerate(ks):
+                op = "sub.cc.u32" if n == 0 else ("subc.cc.u32" if n < len(ks) - 1 else "subc.u32")
+                if len(ks) == 1:
+                    op = "sub.u32"
+                lines.append(f"{op} %{n}, %{n}, %{len(ks) + n};")
+            w('        asm("' + '\\n\\t"\n            "'.join(lines) + '"\n')
+            w("            : " + ", ".join(f'"+r"(r[{k}])' for k in ks) + "\n")
+            w("            : " + ", ".join(f'"r"(q[{k - j}])' for k in ks) + ");\n")
+            w("    }\n")
     w("}\n#endif  // __CUDA_ARCH__\n\n}  // namespace hodor\n")
 
 
