@@ -320,7 +320,7 @@ struct Ops {
         }
         {
             ProfScope ps(c, st, LAST ? "ntt_pass_last" : (SCALE_IN ? "ntt_pass_first_scaled" : "ntt_pass"));
-            kern<<<grid, 1 << B, smem, st>>>(p);
+            kern<<<grid, PassOccupancy<B>::THREADS, smem, st>>>(p);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;

@@ -165,47 +165,93 @@ DEV void dif_inreg(const Field<F>& fld, Fe (&x)[1 << LOGR], const NttPass& p, ui
     }
 }
 
+// How a 2^B-point block transform is split into register-resident radix-2^W butterflies: up to four
+// groups, widths R1..R4 summing to B.  With radix-8 groups a thread keeps 8 elements live through the
+// butterfly (124-128 registers: 2 blocks of 256 threads per SM); with radix-4 groups only 4 (68-72
+// registers: 3 blocks per SM) for the same number of multiplies per element (B = 8: 3.25 either
+// way), and the extra resident warps are what keeps the multiplier pipe fed while other warps sit
+// in loads, barriers and add/sub work: measured 24.97 vs 26.66 ms on the 2^24 x 8 coset LDE.
+// B = 9 (128 KiB tile: one block per SM whatever the register count) and B = 6 stay radix-8.
+#ifndef HODOR_RADIX4_GROUPS
+#define HODOR_RADIX4_GROUPS 1
+#endif
 template <int B>
 struct Groups {
-    static constexpr int R1 = 3;
+    static constexpr bool RADIX4 = HODOR_RADIX4_GROUPS && (B == 7 || B == 8);
+    static constexpr int R1 = RADIX4 ? (B == 8 ? 2 : 1) : 3;
     static constexpr int REM = B - 3;
-    static constexpr int R2 = REM <= 3 ? REM : (REM + 1) / 2;
-    static constexpr int R3 = REM - R2;
-    static constexpr int NGROUPS = R3 > 0 ? 3 : 2;
+    static constexpr int R2 = RADIX4 ? 2 : (REM <= 3 ? REM : (REM + 1) / 2);
+    static constexpr int R3 = RADIX4 ? 2 : REM - R2;
+    static constexpr int R4 = B - R1 - R2 - R3;
+    static constexpr int NGROUPS = R4 > 0 ? 4 : (R3 > 0 ? 3 : 2);
+};
+
+// Resident blocks per SM the pass kernel is compiled for (8 * 2^B / EPT threads, EPT elements per
+// thread, 2^B x 256 B of shared memory).  B = 8, the 2^24 workhorse: 3 x 256 threads at <= 85
+// registers and 3 x 64 KiB, so that other blocks' multiplier work covers one block's loads and
+// barrier waits.  HODOR_B8_EPT4: 2 x 512 threads with 4 elements each (<= 64 registers).
+#ifndef HODOR_B8_EPT4
+#define HODOR_B8_EPT4 0
+#endif
+template <int B>
+struct PassOccupancy {
+    static constexpr int EPT = (HODOR_B8_EPT4 && B == 8 && Groups<8>::RADIX4) ? 4 : 8;
+    static constexpr int THREADS = (8 << B) / EPT;
+    static constexpr int MIN_BLOCKS =
+        B >= 9 ? 1 : (B == 8 ? (EPT == 4 ? 2 : (Groups<8>::RADIX4 ? 3 : 2)) : (B == 7 ? (Groups<7>::RADIX4 ? 6 : 4) : 8));
 };
 
 // One group of the block-local NTT: every thread owns 8 elements = 8 >> LOGR butterflies of radix
-// 2^LOGR whose members are 2^SL positions apart.  SRC/DST: 0 = shared tile, 1 = global.
-template <class F, int B, int LOGR, int SL, int TWSH, bool FROM_GLOBAL, bool TO_GLOBAL, class LoadG, class StoreG>
+// 2^LOGR whose members are 2^SL positions apart.  FROM_GLOBAL / TO_GLOBAL: the group reads its inputs
+// from / writes its outputs to HBM instead of the shared tile.
+//
+// Code size matters here: with every multiply inlined and every loop unrolled a pass kernel is
+// 210-260 KB of straight-line code, far beyond the instruction cache, and ncu attributes 7-13 % of
+// the issue stalls to `no_instruction`.  So only the butterflies (whose twiddles are compile-time
+// selected constants) are unrolled; every per-element table multiply -- coset scaling on load,
+// inter-group twiddle, inter-pass twiddle on store -- runs in a rolled loop over the thread's own
+// slots of the shared tile (owner-only accesses: no barrier needed), one multiplier body each.
+template <class F, int B, int LOGR, int SL, int TWSH, bool FROM_GLOBAL, bool MUL_ON_LOAD, bool TO_GLOBAL, class LoadG,
+          class StoreG>
 DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t tid, uint32_t oz, LoadG&& load_global,
                    StoreG&& store_global) {
     constexpr int R = 1 << LOGR;
-    constexpr int NB = 8 / R;
-    constexpr uint32_t T = 1u << B;
+    constexpr int EPT = PassOccupancy<B>::EPT;  // elements per thread
+    static_assert(EPT >= R, "a thread holds at least one whole butterfly");
+    constexpr int NB = EPT / R;
+    constexpr uint32_t T = (8u << B) / EPT;  // threads per block
     constexpr uint32_t PLANE = 8u << B;
-#pragma unroll
+    constexpr uint32_t STEP = 8u << SL;  // slots between members of one butterfly
+#pragma unroll 1
     for (int j = 0; j < NB; j++) {
         const uint32_t q = tid + j * T;
         const uint32_t c = q & 7u, rest = q >> 3;
         const uint32_t lo = rest & ((1u << SL) - 1u), hi = rest >> SL;
         const uint32_t base = (hi << (SL + LOGR)) | lo;
+        const uint32_t slot0 = base * 8 + c;
         Fe x[R];
+        if constexpr (FROM_GLOBAL && MUL_ON_LOAD) {
+#pragma unroll 1
+            for (uint32_t d = 0; d < (uint32_t)R; d++) sts_fe(sm, PLANE, slot0 + d * STEP, load_global(base + (d << SL), c));
+        }
 #pragma unroll
         for (int d = 0; d < R; d++) {
-            const uint32_t pos = base + ((uint32_t)d << SL);
-            if constexpr (FROM_GLOBAL) x[d] = load_global(pos, c);
-            else x[d] = lds_fe(sm, PLANE, pos * 8 + c);
+            if constexpr (FROM_GLOBAL && !MUL_ON_LOAD) x[d] = load_global(base + ((uint32_t)d << SL), c);
+            else x[d] = lds_fe(sm, PLANE, slot0 + d * STEP);
         }
         dif_inreg<F, LOGR>(fld, x, p, oz);
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            Fe v = x[bitrev_c(k, LOGR)];
-            const uint32_t pos = base + ((uint32_t)k << SL);
-            if constexpr (SL > 0) {
-                if (k > 0) v = mul_by(fld, v, ld_pre(p.tw_b, (size_t)((k * lo) << TWSH)));
+        for (int k = 0; k < R; k++) sts_fe(sm, PLANE, slot0 + k * STEP, x[bitrev_c(k, LOGR)]);
+        if constexpr (SL > 0 || TO_GLOBAL) {
+#pragma unroll 1
+            for (uint32_t k = TO_GLOBAL ? 0u : 1u; k < (uint32_t)R; k++) {
+                Fe v = lds_fe(sm, PLANE, slot0 + k * STEP);
+                if constexpr (SL > 0) {
+                    if (k > 0) v = mul_by(fld, v, ld_pre(p.tw_b, (size_t)((k * lo) << TWSH)));
+                }
+                if constexpr (TO_GLOBAL) store_global(base + (k << SL), c, v);
+                else sts_fe(sm, PLANE, slot0 + k * STEP, v);
             }
-            if constexpr (TO_GLOBAL) store_global(pos, c, v);
-            else sts_fe(sm, PLANE, pos * 8 + c, v);
         }
     }
 }
@@ -214,23 +260,16 @@ DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t ti
 template <int B>
 DEV uint32_t local_out_index(uint32_t pos) {
     using G = Groups<B>;
-    constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3;
-    const uint32_t k1 = pos >> (R2 + R3);
-    const uint32_t k2 = (pos >> R3) & ((1u << R2) - 1u);
-    const uint32_t k3 = pos & ((1u << R3) - 1u);
-    return k1 | (k2 << R1) | (k3 << (R1 + R2));
+    constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3, R4 = G::R4;
+    const uint32_t k1 = pos >> (R2 + R3 + R4);
+    const uint32_t k2 = (pos >> (R3 + R4)) & ((1u << R2) - 1u);
+    const uint32_t k3 = (pos >> R4) & ((1u << R3) - 1u);
+    const uint32_t k4 = pos & ((1u << R4) - 1u);
+    return k1 | (k2 << R1) | (k3 << (R1 + R2)) | (k4 << (R1 + R2 + R3));
 }
 
-// Resident blocks per SM the pass kernel is compiled for: 2^B threads x 8 elements in registers.
-// B = 8 (the 2^24 workhorse): 2 x 256 threads at <= 128 registers and 2 x 64 KiB of shared memory,
-// so one block's global loads / barrier waits overlap the other's multiplier work.
-template <int B>
-struct PassOccupancy {
-    static constexpr int MIN_BLOCKS = B >= 9 ? 1 : (B == 8 ? 2 : (B == 7 ? 4 : 8));
-};
-
 template <class F, int B, bool SCALE_IN, bool LAST>
-__global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass_kernel(const __grid_constant__ NttPass p) {
+__global__ void __launch_bounds__(PassOccupancy<B>::THREADS, PassOccupancy<B>::MIN_BLOCKS) ntt_pass_kernel(const __grid_constant__ NttPass p) {
     using G = Groups<B>;
     extern __shared__ uint4 sm[];
     const uint32_t tid = threadIdx.x;
@@ -314,15 +353,21 @@ __global__ void __launch_bounds__(1 << B, PassOccupancy<B>::MIN_BLOCKS) ntt_pass
         }
     };
 
-    constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3;
-    ntt_group<F, B, R1, B - R1, 0, true, false>(fld, p, sm, tid, oz, load_global, store_global);
+    constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3, R4 = G::R4;
+    ntt_group<F, B, R1, B - R1, 0, true, SCALE_IN, false>(fld, p, sm, tid, oz, load_global, store_global);
     __syncthreads();
     if constexpr (G::NGROUPS == 2) {
-        ntt_group<F, B, R2, 0, R1, false, true>(fld, p, sm, tid, oz, load_global, store_global);
-    } else {
-        ntt_group<F, B, R2, R3, R1, false, false>(fld, p, sm, tid, oz, load_global, store_global);
+        ntt_group<F, B, R2, 0, R1, false, false, true>(fld, p, sm, tid, oz, load_global, store_global);
+    } else if constexpr (G::NGROUPS == 3) {
+        ntt_group<F, B, R2, R3, R1, false, false, false>(fld, p, sm, tid, oz, load_global, store_global);
         __syncthreads();
-        ntt_group<F, B, R3, 0, R1 + R2, false, true>(fld, p, sm, tid, oz, load_global, store_global);
+        ntt_group<F, B, R3, 0, R1 + R2, false, false, true>(fld, p, sm, tid, oz, load_global, store_global);
+    } else {
+        ntt_group<F, B, R2, R3 + R4, R1, false, false, false>(fld, p, sm, tid, oz, load_global, store_global);
+        __syncthreads();
+        ntt_group<F, B, R3, R4, R1 + R2, false, false, false>(fld, p, sm, tid, oz, load_global, store_global);
+        __syncthreads();
+        ntt_group<F, B, R4, 0, R1 + R2 + R3, false, false, true>(fld, p, sm, tid, oz, load_global, store_global);
     }
 }
 
