@@ -83,6 +83,7 @@ _SIGS = {
     "hodor_cuda_ifft": (C.c_int, [u64p, C.c_uint32, C.c_int, C.c_int]),
     "hodor_cuda_distribute_powers": (C.c_int, [u64p, C.c_uint64, u64p, C.c_int]),
     "hodor_cuda_lde": (C.c_int, [u64p, C.c_uint32, C.c_uint32, C.c_int, u64p, C.c_int]),
+    "hodor_cuda_lde_batch": (C.c_int, [C.POINTER(u64p), C.POINTER(u64p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "hodor_cuda_elementwise": (C.c_int, [C.c_int, u64p, u64p, u64p, C.c_uint64, C.c_int]),
     "hodor_cuda_batch_inversion": (C.c_int, [u64p, C.c_uint64, C.c_int]),
     "hodor_cuda_evaluate_at": (C.c_int, [u64p, C.c_uint64, u64p, u64p, C.c_int]),

@@ -239,6 +239,8 @@ int hodor_cuda_init(int device) {
     std::unique_ptr<Ctx> c(new Ctx());
     c->device = device;
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaMalloc((void**)&c->small, 4096));
     c->key = b2s_keyed_state();
     if (const char* mb = getenv("HODOR_TABLE_BUDGET_MB")) c->full_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
@@ -269,6 +271,8 @@ void hodor_cuda_shutdown(void) {
     for (auto e : g_ctx->event_pool) cudaEventDestroy(e);
     cudaFree(g_ctx->small);
     cudaStreamDestroy(g_ctx->stream);
+    cudaStreamDestroy(g_ctx->copy_in);
+    cudaStreamDestroy(g_ctx->copy_out);
     delete g_ctx;
     g_ctx = nullptr;
 }
@@ -618,6 +622,67 @@ int hodor_cuda_lde(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, 
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[1], total * 32, cudaMemcpyDeviceToHost, c->stream));
     HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+// `count` LDEs of the same shape, software-pipelined over three streams with double-buffered device
+// staging: H2D of polynomial i+1 and D2H of polynomial i-1 run while polynomial i is transformed, so
+// a prover lifting all its registers (src/prover/mod.rs:73-76 loops `w.lde(..)`) pays
+// max(PCIe, compute) per polynomial instead of their sum.  Host buffers should be pinned
+// (hodor_cuda_host_alloc) -- pageable memory makes the copies synchronous and serialises the pipe.
+int hodor_cuda_lde_batch(const uint64_t* const* coeffs, uint64_t* const* outs, uint32_t count, uint32_t log_n,
+                         uint32_t log_factor, int coset, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 32 || log_n + log_factor > 34) return fail(HODOR_ERR_INVALID_ARG, "LDE too large");
+    if (count == 0) return HODOR_OK;
+    if (coeffs == nullptr || outs == nullptr) return fail(HODOR_ERR_INVALID_ARG, "lde_batch: NULL pointer table");
+    for (uint32_t i = 0; i < count; i++)
+        if (coeffs[i] == nullptr || outs[i] == nullptr) return fail(HODOR_ERR_INVALID_ARG, "lde_batch: NULL buffer");
+    const size_t n = (size_t)1 << log_n, total = n << log_factor;
+    const uint32_t nbuf = count < 2 ? 1 : 2;
+    void* in_buf[2] = {nullptr, nullptr};
+    void* out_buf[2] = {nullptr, nullptr};
+    cudaEvent_t in_done[2], comp_done[2], out_done[2];
+    int rc = HODOR_OK;
+    for (uint32_t b = 0; b < nbuf && rc == HODOR_OK; b++) {
+        in_buf[b] = c->pool_alloc(n * 32);
+        out_buf[b] = c->pool_alloc(total * 32);
+        if (!in_buf[b] || !out_buf[b]) rc = HODOR_ERR_OOM;
+    }
+    for (uint32_t b = 0; b < nbuf; b++) {
+        cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming);
+    }
+    auto step = [&](uint32_t i) -> int {
+        const uint32_t b = i % nbuf;
+        if (i >= nbuf) HODOR_CUDA_TRY(cudaStreamWaitEvent(c->copy_in, comp_done[b], 0));  // in_buf[b] consumed
+        HODOR_CUDA_TRY(cudaMemcpyAsync(in_buf[b], coeffs[i], n * 32, cudaMemcpyHostToDevice, c->copy_in));
+        HODOR_CUDA_TRY(cudaEventRecord(in_done[b], c->copy_in));
+        HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, in_done[b], 0));
+        if (i >= nbuf) HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, out_done[b], 0));  // out_buf[b] drained
+        int r = do_lde(*c, ops, (const uint4*)in_buf[b], (uint4*)out_buf[b], log_n, log_factor, coset, c->stream);
+        if (r) return r;
+        HODOR_CUDA_TRY(cudaEventRecord(comp_done[b], c->stream));
+        HODOR_CUDA_TRY(cudaStreamWaitEvent(c->copy_out, comp_done[b], 0));
+        HODOR_CUDA_TRY(cudaMemcpyAsync(outs[i], out_buf[b], total * 32, cudaMemcpyDeviceToHost, c->copy_out));
+        HODOR_CUDA_TRY(cudaEventRecord(out_done[b], c->copy_out));
+        return HODOR_OK;
+    };
+    for (uint32_t i = 0; i < count && rc == HODOR_OK; i++) rc = step(i);
+    // drain everything before the staging buffers go back to the pool, error or not
+    cudaStreamSynchronize(c->copy_in);
+    cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->copy_out);
+    for (uint32_t b = 0; b < nbuf; b++) {
+        cudaEventDestroy(in_done[b]);
+        cudaEventDestroy(comp_done[b]);
+        cudaEventDestroy(out_done[b]);
+        if (in_buf[b]) c->pool_free(in_buf[b]);
+        if (out_buf[b]) c->pool_free(out_buf[b]);
+    }
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "lde_batch");
     return HODOR_OK;
 }
 int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id) {

@@ -53,6 +53,7 @@ struct NttTables {
 struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined batch entry points
     std::mutex mu;
     void* ws = nullptr;
     size_t ws_bytes = 0;

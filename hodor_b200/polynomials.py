@@ -194,3 +194,25 @@ class Polynomial:
         out = np.zeros(4, np.uint64)
         check(lib.hodor_cuda_evaluate_at(_p(self.coeffs), C.c_uint64(self.size()), _p(fld.limbs(g)), _p(out), self.field_id))
         return out
+
+
+def lde_batch(polys, worker: Optional[Worker], factor: int, coset: bool = False):
+    """`[w.lde(worker, factor) for w in polys]` (src/prover/mod.rs:73-76) as ONE pipelined call:
+    copies of neighbouring polynomials overlap the transform of the current one."""
+    polys = list(polys)
+    if not polys:
+        return []
+    fid, n = polys[0].field_id, polys[0].size()
+    for q in polys:
+        q._need(COEFFICIENTS)
+        assert q.field_id == fid and q.size() == n, "lde_batch: polynomials must share field and size"
+    if factor < 1 or factor & (factor - 1):
+        raise AssertionError("assert!(factor.is_power_of_two())")
+    ensure_init()
+    Domain.new_for_size(fid, n * factor)
+    outs = [np.zeros((n * factor, 4), np.uint64) for _ in polys]
+    u64p = C.POINTER(C.c_uint64)
+    ins_arr = (u64p * len(polys))(*[_p(q.coeffs) for q in polys])
+    outs_arr = (u64p * len(polys))(*[_p(o) for o in outs])
+    check(lib.hodor_cuda_lde_batch(ins_arr, outs_arr, len(polys), polys[0].exp, factor.bit_length() - 1, int(coset), fid))
+    return [Polynomial(fid, o, VALUES) for o in outs]

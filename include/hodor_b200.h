@@ -101,6 +101,13 @@ int hodor_cuda_distribute_powers(uint64_t* a, uint64_t n, const uint64_t g[4], i
  * (src/polynomials/mod.rs:343-352, 418-482, 544-609): out has n << log_factor elements,
  * out[i + L*k] = P(shift * w_{nL}^(i + L*k)), shift = 1 or multiplicative_generator. */
 int hodor_cuda_lde(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint64_t* out, int field_id);
+/* The same LDE for `count` polynomials of one shape (the prover lifts every register:
+ * `for w in witness { w.lde(&worker, lde_factor) }`, src/prover/mod.rs:73-76), pipelined so that the
+ * host<->device copies of neighbouring polynomials overlap the transform of the current one.
+ * coeffs[i]: 2^log_n elements, outs[i]: 2^(log_n+log_factor) elements; pinned host memory
+ * (hodor_cuda_host_alloc) is needed for the overlap, pageable memory still gives correct results. */
+int hodor_cuda_lde_batch(const uint64_t* const* coeffs, uint64_t* const* outs, uint32_t count, uint32_t log_n,
+                         uint32_t log_factor, int coset, int field_id);
 /* elementwise Polynomial ops (src/polynomials/mod.rs:640-683, 817-887): op 0 mul, 1 add, 2 sub,
  * 3 scale (b is one element).  out may alias a. */
 int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id);

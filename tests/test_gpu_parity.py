@@ -225,6 +225,23 @@ def test_lde_matches_oracle(hodor, oracle, fid, coset):
         assert np.array_equal(got, oracle.lde(fid, a, log_n, L, coset)), (log_n, L)
 
 
+def test_lde_batch_pipelined_matches_single_calls(hodor, oracle):
+    """hodor_cuda_lde_batch: N polynomials through the double-buffered copy/compute pipeline give the
+    bits of N separate calls (and of the oracle); batch sizes around the double-buffer depth."""
+    fid, log_n, L = 0, 13, 4
+    polys = [oracle.random_elements(fid, 1 << log_n, seed=60 + i) for i in range(5)]
+    for count in (0, 1, 2, 3, 5):
+        for coset in (False, True):
+            got = hodor.lde_batch([hodor.Polynomial.from_coeffs(fid, a) for a in polys[:count]], hodor.Worker(), L, coset)
+            assert len(got) == count
+            for a, g in zip(polys, got):
+                assert np.array_equal(g.as_ref(), oracle.lde(fid, a, log_n, L, coset))
+    big = [oracle.random_elements(fid, 1 << 20, seed=70 + i) for i in range(3)]
+    got = hodor.lde_batch([hodor.Polynomial.from_coeffs(fid, a) for a in big], hodor.Worker(), 8, True)
+    for a, g in zip(big, got):
+        assert np.array_equal(g.as_ref(), hodor.Polynomial.from_coeffs(fid, a).coset_lde(hodor.Worker(), 8).as_ref())
+
+
 def test_lde_2p20_x8_bit_exact_and_horner(hodor, oracle, pymodel):
     """configs[1] shape at a size the CPU oracle finishes in seconds: coset LDE, blowup 8."""
     fid, log_n, L = 0, 18, 8
