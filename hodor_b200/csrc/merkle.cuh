@@ -37,23 +37,69 @@ HD constexpr int b2s_sigma(int r, int i) {
     return s[r][i];
 }
 
-HD uint32_t rotr32(uint32_t x, int r) {
+// Rotations.  HODOR_B2S_ROT selects how the device does them (all bit-identical):
+//   0  funnel shift (SHF.R.W) for all four amounts
+//   1  byte permute (PRMT) for 16 and 8, funnel shift for 12 and 7
+//   2  PRMT for 16 and 8; 12 and 7 as x * 2^(32-r) on the multiplier pipe: the two halves of the 64-bit
+//      product are x >> r and x << (32-r) and never overlap, so their sum is the rotation
+//   3  the multiplier form for all four
+#ifndef HODOR_B2S_ROT
+#define HODOR_B2S_ROT 0
+#endif
+#if defined(__CUDACC__) && HODOR_B2S_ROT >= 2
+// multipliers 2^(32-r) for r = 16, 12, 8, 7 in constant memory, so that ptxas cannot turn the product back into a shift
+__constant__ uint32_t k_b2s_rot_mul[4] = {1u << 16, 1u << 20, 1u << 24, 1u << 25};
+#endif
+template <int R>
+HD uint32_t rotr32c(uint32_t x) {
 #ifdef __CUDA_ARCH__
-    return __funnelshift_r(x, x, r);
+#if HODOR_B2S_ROT == 1 || HODOR_B2S_ROT == 2
+    if constexpr (R == 16) return __byte_perm(x, x, 0x1032);
+    if constexpr (R == 8) return __byte_perm(x, x, 0x0321);
+#endif
+#if HODOR_B2S_ROT >= 2
+    {
+        const unsigned long long w = (unsigned long long)x * k_b2s_rot_mul[R == 16 ? 0 : (R == 12 ? 1 : (R == 8 ? 2 : 3))];
+        return (uint32_t)w + (uint32_t)(w >> 32);
+    }
 #else
-    return (x >> r) | (x << (32 - r));
+    return __funnelshift_r(x, x, R);
+#endif
+#else
+    return (x >> R) | (x << (32 - R));
 #endif
 }
 
-#define HODOR_B2S_G(a, b, c, d, x, y) \
-    v[a] = v[a] + v[b] + (x);         \
-    v[d] = rotr32(v[d] ^ v[a], 16);   \
+// Three-input additions a + b + m.  The ALU pipe (LOP3 / SHF / IADD3, 64 lanes per clock per SM) is
+// what bounds the compression; ptxas already moves the two-input additions to the multiplier pipe
+// as IMAD.IADD.  HODOR_B2S_ADD3 = 1 does the same for the three-input ones, as two multiply-adds by an
+// opaque 1 from constant memory.
+// Measured on B200 (tools/microbench.cu): node hash 22.8 -> 27.6, leaf hash 25.0 -> 27.2 G compressions/s.
+#ifndef HODOR_B2S_ADD3
+#define HODOR_B2S_ADD3 1
+#endif
+#if defined(__CUDACC__) && HODOR_B2S_ADD3
+__constant__ uint32_t k_b2s_one = 1u;
+#endif
+// m_is_zero: known at compile time after unrolling (the zero half of a 32-byte leaf message)
+HD uint32_t b2s_add3(uint32_t a, uint32_t b, uint32_t m, bool m_is_zero) {
+    if (m_is_zero) return a + b;
+#if defined(__CUDA_ARCH__) && HODOR_B2S_ADD3
+    return (a * k_b2s_one + b) * k_b2s_one + m;
+#else
+    return a + b + m;
+#endif
+}
+
+#define HODOR_B2S_G(a, b, c, d, x, y, zx, zy) \
+    v[a] = b2s_add3(v[a], v[b], (x), (zx)); \
+    v[d] = rotr32c<16>(v[d] ^ v[a]);  \
     v[c] = v[c] + v[d];               \
-    v[b] = rotr32(v[b] ^ v[c], 12);   \
-    v[a] = v[a] + v[b] + (y);         \
-    v[d] = rotr32(v[d] ^ v[a], 8);    \
+    v[b] = rotr32c<12>(v[b] ^ v[c]);  \
+    v[a] = b2s_add3(v[a], v[b], (y), (zy)); \
+    v[d] = rotr32c<8>(v[d] ^ v[a]);   \
     v[c] = v[c] + v[d];               \
-    v[b] = rotr32(v[b] ^ v[c], 7);
+    v[b] = rotr32c<7>(v[b] ^ v[c]);
 
 // One Blake2s compression (RFC 7693 3.2).  m[] indices are compile-time after unrolling, so the
 // message stays in registers; with HALF only m[0..7] are non-zero (32-byte leaf message).
@@ -69,16 +115,18 @@ HD void b2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint32_t t0, boo
     if (last) v[14] = ~v[14];
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-#define MSG(i) ((HALF && b2s_sigma(r, i) >= 8) ? 0u : m[b2s_sigma(r, i)])
-        HODOR_B2S_G(0, 4, 8, 12, MSG(0), MSG(1))
-        HODOR_B2S_G(1, 5, 9, 13, MSG(2), MSG(3))
-        HODOR_B2S_G(2, 6, 10, 14, MSG(4), MSG(5))
-        HODOR_B2S_G(3, 7, 11, 15, MSG(6), MSG(7))
-        HODOR_B2S_G(0, 5, 10, 15, MSG(8), MSG(9))
-        HODOR_B2S_G(1, 6, 11, 12, MSG(10), MSG(11))
-        HODOR_B2S_G(2, 7, 8, 13, MSG(12), MSG(13))
-        HODOR_B2S_G(3, 4, 9, 14, MSG(14), MSG(15))
+#define MSGZ(i) (HALF && b2s_sigma(r, i) >= 8)
+#define MSG(i) (MSGZ(i) ? 0u : m[b2s_sigma(r, i)])
+        HODOR_B2S_G(0, 4, 8, 12, MSG(0), MSG(1), MSGZ(0), MSGZ(1))
+        HODOR_B2S_G(1, 5, 9, 13, MSG(2), MSG(3), MSGZ(2), MSGZ(3))
+        HODOR_B2S_G(2, 6, 10, 14, MSG(4), MSG(5), MSGZ(4), MSGZ(5))
+        HODOR_B2S_G(3, 7, 11, 15, MSG(6), MSG(7), MSGZ(6), MSGZ(7))
+        HODOR_B2S_G(0, 5, 10, 15, MSG(8), MSG(9), MSGZ(8), MSGZ(9))
+        HODOR_B2S_G(1, 6, 11, 12, MSG(10), MSG(11), MSGZ(10), MSGZ(11))
+        HODOR_B2S_G(2, 7, 8, 13, MSG(12), MSG(13), MSGZ(12), MSGZ(13))
+        HODOR_B2S_G(3, 4, 9, 14, MSG(14), MSG(15), MSGZ(14), MSGZ(15))
 #undef MSG
+#undef MSGZ
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
@@ -137,6 +185,32 @@ HD Digest hash_node64(const B2sState& key, const Digest& l, const Digest& r) {
     return d;
 }
 
+// Out-of-line copies for the tree kernels.  A thread-serial subtree of 2^3 leaves is 15 compressions;
+// inlined that is ~240 KB of straight-line code per kernel and ncu shows 6 `no_instruction` stall
+// cycles per issued instruction (profiles/r01_final_ncu_merkle).  Two shared ~16 KB bodies stay in the
+// instruction cache; the call passes 16-24 registers, against ~1000 instructions of work.
+#ifndef HODOR_B2S_OUT_OF_LINE
+#define HODOR_B2S_OUT_OF_LINE 1
+#endif
+#if defined(__CUDACC__)
+static __device__ __noinline__ Digest hash_leaf32_ool(B2sState key, Digest leaf) { return hash_leaf32(key, leaf.w); }
+static __device__ __noinline__ Digest hash_node64_ool(B2sState key, Digest l, Digest r) { return hash_node64(key, l, r); }
+DEV Digest tree_hash_leaf(const B2sState& key, const Digest& leaf) {
+#if HODOR_B2S_OUT_OF_LINE
+    return hash_leaf32_ool(key, leaf);
+#else
+    return hash_leaf32(key, leaf.w);
+#endif
+}
+DEV Digest tree_hash_node(const B2sState& key, const Digest& l, const Digest& r) {
+#if HODOR_B2S_OUT_OF_LINE
+    return hash_node64_ool(key, l, r);
+#else
+    return hash_node64(key, l, r);
+#endif
+}
+#endif
+
 DEV Digest ld_digest(const uint4* base, size_t idx) {
     const uint4 a = base[2 * idx], b = base[2 * idx + 1];
     Digest d;
@@ -156,12 +230,12 @@ template <int K, bool LEAF>
 DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, size_t w_in, size_t first) {
     if constexpr (K == 0) {
         const Digest raw = ld_digest(in, first);
-        if constexpr (LEAF) return hash_leaf32(key, raw.w);
+        if constexpr (LEAF) return tree_hash_leaf(key, raw);
         else return raw;
     } else {
         const Digest l = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first);
         const Digest r = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first + ((size_t)1 << (K - 1)));
-        const Digest d = hash_node64(key, l, r);
+        const Digest d = tree_hash_node(key, l, r);
         st_digest(nodes, (w_in >> K) + (first >> K), d);
         return d;
     }
