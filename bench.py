@@ -190,6 +190,29 @@ def run_reference(args, rank: int):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def gpu_local_cpus(local_rank: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None.  Pinned staging buffers allocated from a
+    thread bound there are local to the GPU's PCIe root: with one rank per GPU and unbound processes the
+    buffers of all ranks can land on one socket and every copy then crosses the inter-socket link."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        text = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        node = open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip()
+        return (cpus, node) if cpus else None
+    except Exception:
+        return None
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
@@ -266,10 +289,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (profiles/)
     traffic, pipes = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom["name"]]
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))[dom["name"]]
         traffic = cap["traffic"]
-        pipes = {"fma_pipe_cycles_active_pct": cap["fma_pipe_cycles_active_pct"], "alu_pipe_inst_pct": cap["alu_pipe_inst_pct"],
-                 "source": "profiles/r01_traffic.json (ncu)"}
+        pipes = {"fmaheavy_pipe_cycles_active_pct": cap["fmaheavy_pipe_cycles_active_pct"],
+                 "alu_pipe_cycles_active_pct": cap["alu_pipe_cycles_active_pct"], "issue_active_pct": cap["issue_active_pct"],
+                 "source": "profiles/r01b_traffic.json (ncu --set full of the same kernel; tools/capture_profiles.sh)"}
     except Exception:
         pass
     roofline = {
@@ -280,7 +304,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                         "share": r["total_ms"] / kern_total} for k, r in prof.items()},
         "job": {"algorithmic_bytes": 32 * n + 32 * n * L, "achieved": (32 * n + 32 * n * L) / (ms_per_step * 1e-3) / 1e9,
                 "frac": (32 * n + 32 * n * L) / (ms_per_step * 1e-3) / 1e9 / peak_gbs},
-        "note": "compute (INT32 issue) bound by design: ~13 256-bit Montgomery multiplies per 64 B moved; see DESIGN.md",
+        "note": "INT32 multiplier-pipe bound by design: ~13 256-bit modular multiplies per 64 B moved (ncu: fmaheavy pipe "
+                "72-78 % busy, DRAM 11-22 %); traffic exceeds the algorithmic bytes because every multiply streams a "
+                "64-byte precomputed table entry instead of spending a second multiplication; see DESIGN.md",
     }
 
     # ---- plain forward NTT 2^24 (BASELINE metric, first half)
@@ -328,8 +354,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # batch entry point: e2e_steps polynomials, each copied in, transformed and copied out inside the
     # timed region, with the copies of neighbouring polynomials overlapping the transform.  The
     # one-polynomial-per-call figure (nothing to overlap with) is reported next to it.
+    all_cpus = os.sched_getaffinity(0)
+    near = gpu_local_cpus(local_rank)
+    if near:
+        os.sched_setaffinity(0, near[0])  # allocate (first-touch) the pinned buffers on the GPU's NUMA node
     h_in = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
     h_outs = [torch.empty((n * L, 4), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    for h in h_outs:
+        h.zero_()
     h_in.numpy().view(np.uint64)[:] = coeffs
     e2e_steps = max(2, args.steps)
 
@@ -365,8 +397,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
            "single_call": {"api": "hodor_cuda_lde (one polynomial per call)", "ms_per_step": single_ms,
                            "value": world * n * L / (single_ms * 1e-3)},
            "timer": "host perf_counter around the synchronous C-ABI call, max over ranks",
+           "host_buffers": (f"pinned, allocated on NUMA node {near[1]} next to the GPU ({len(near[0])} CPUs)"
+                            if near and near[1] not in ("-1", "") else "pinned; the box exposes no NUMA topology"),
            "matches_device_result": same}
     del h_in, h_outs
+    os.sched_setaffinity(0, all_cpus)
 
     # ---- the sharded four-step NTT (only path with a collective), N > 1
     sharded = None
