@@ -661,10 +661,21 @@ struct Ops {
         if (rc) return rc;
         const size_t half = n / 2;
         const unsigned grid = (unsigned)((half + 255) / 256 > 148 * 16 ? 148 * 16 : (half + 255) / 256);
+        // flat fixed-operand table of omega_N^-e, e < N/2 (32 * N bytes; the device-side `omegas_inv`),
+        // for the domains where the chain is long enough to pay for it; cached and budgeted like the
+        // other expanded tables, two-level fallback otherwise
+        const uint4* flat = nullptr;
+        if (log_n0 >= 16)
+            flat = get_full_table(c, key_of("ffull", log_n0, 0, &omega_inv, 1), t->two_level(), 0, 0, (size_t)1 << (log_n0 - 1),
+                                  1, -1, st);
         {
             ProfScope ps(c, st, "fri_fold");
-            fri_fold_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), layer, chal, idx_offset,
-                                                                idx_stride, 0u);
+            if (flat)
+                fri_fold_kernel<F, true><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), flat, layer, chal,
+                                                                           idx_offset, idx_stride, 0u);
+            else
+                fri_fold_kernel<F, false><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), nullptr, layer,
+                                                                            chal, idx_offset, idx_stride, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;

@@ -15,22 +15,34 @@
 
 namespace hodor {
 
-template <class F>
 // `in` holds the slice v[idx_offset + idx_stride * t] of the layer (offset 0, stride 1: the whole
 // layer; offset r, stride G: rank r's cyclic slice of a layer sharded over G GPUs, whose fold pairs
 // (t, t + half) are then both local).
+// FLAT: the twiddle omega_N^-e is one 64-byte fixed-operand entry of a flat N/2-entry table (the
+// reference's own `omegas_inv`, :24-40) instead of hi * lo from the two-level table; both remaining
+// multiplies then go through Field::mul_pre (the challenge is converted once per thread): 1.3
+// Montgomery-multiply equivalents per output instead of 3.
+template <class F, bool FLAT>
 __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* out, size_t half, TwoLevel winv,
-                                                       uint32_t layer, const uint4* challenge, uint64_t idx_offset,
-                                                       uint64_t idx_stride, uint32_t zero) {
+                                                       const uint4* winv_flat, uint32_t layer, const uint4* challenge,
+                                                       uint64_t idx_offset, uint64_t idx_stride, uint32_t zero) {
     const Field<F> fld(threadIdx.x & zero);
     const Fe c = ld_fe(challenge, 0);
+    FePre cp;
+    if constexpr (FLAT) fld.make_pre(c, cp.w, cp.q);
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += (size_t)gridDim.x * blockDim.x) {
         const size_t idx = t;
         const Fe f0 = ld_fe(in, idx), f1 = ld_fe(in, idx + half);
         const Fe even = fld.add(f0, f1);
         Fe odd = fld.sub(f0, f1);
-        odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, (idx_offset + idx_stride * (uint64_t)t) << layer));
-        odd = fld.mul(odd, c);
+        const uint64_t e = (idx_offset + idx_stride * (uint64_t)t) << layer;
+        if constexpr (FLAT) {
+            odd = mul_by(fld, odd, ld_pre(winv_flat, (size_t)e));
+            odd = mul_by(fld, odd, cp);
+        } else {
+            odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, e));
+            odd = fld.mul(odd, c);
+        }
         st_fe(out, idx, fld.halve(fld.add(odd, even)));
     }
 }
