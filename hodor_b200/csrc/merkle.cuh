@@ -263,24 +263,38 @@ __global__ void __launch_bounds__(1024) merkle_tail_kernel(const uint4* in, uint
         for (int i = 0; i < 8; i++) z.w[i] = 0;
         st_digest(nodes, 0, z);
     }
+    // The top of the tree (heap indices < 1024) is mirrored in shared memory: the chain of levels is
+    // latency bound (one compression, ~0.6 us, per level), and a global store -> barrier -> global load
+    // round trip per level would double that.  `nodes` still receives every digest.
+    __shared__ uint4 heap[2 * 1024];
+    bool children_in_smem = false;  // the level below the one being computed is complete in `heap`
     uint32_t width = w_in / 2;
     if constexpr (LEAF) {
+        children_in_smem = 2 * width <= 1024;
         for (uint32_t i = tid; i < width; i += nt) {
             const Digest a = ld_digest(in, 2 * i), b = ld_digest(in, 2 * i + 1);
-            st_digest(nodes, width + i, hash_node64(key, hash_leaf32(key, a.w), hash_leaf32(key, b.w)));
+            const Digest d = hash_node64(key, hash_leaf32(key, a.w), hash_leaf32(key, b.w));
+            st_digest(nodes, width + i, d);
+            if (children_in_smem) st_digest(heap, width + i, d);
         }
         __syncthreads();
         width /= 2;
     }
     for (; width >= 1; width /= 2) {
+        const bool to_smem = 2 * width <= 1024;
         for (uint32_t i = tid; i < width; i += nt) {
-            const Digest a = ld_digest(nodes, 2 * (size_t)(width + i)), b = ld_digest(nodes, 2 * (size_t)(width + i) + 1);
-            st_digest(nodes, width + i, hash_node64(key, a, b));
+            const uint32_t l = 2 * (width + i);
+            const Digest a = children_in_smem ? ld_digest(heap, l) : ld_digest(nodes, l);
+            const Digest b = children_in_smem ? ld_digest(heap, l + 1) : ld_digest(nodes, (size_t)l + 1);
+            const Digest d = hash_node64(key, a, b);
+            st_digest(nodes, width + i, d);
+            if (to_smem) st_digest(heap, width + i, d);
         }
         __syncthreads();
+        children_in_smem = to_smem;
     }
     if (tid == 0) {
-        const Digest root = ld_digest(nodes, 1);
+        const Digest root = ld_digest(heap, 1);
         if (root_out != nullptr) st_digest(root_out, 0, root);
         if (challenge_out != nullptr) {
             // read_be: digest bytes are one big-endian 256-bit integer; word j (LE load) holds

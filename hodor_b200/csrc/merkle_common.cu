@@ -1,6 +1,8 @@
 // Field-independent part of the Merkle build: the wide levels (thread-serial subtrees) and the
 // authentication-path gather.  Reference: Blake2sIopTree::create / get_path,
 // src/iop/blake2s_trivial_iop.rs:131-219, 251-279.
+#include <cstdlib>
+
 #include "context.h"
 
 namespace hodor {
@@ -14,26 +16,46 @@ static unsigned grid_for(size_t work_items, unsigned block) {
 
 template <int K, bool LEAF>
 static int launch_levels(Ctx& c, const uint4* in, uint4* nodes, size_t w_in, cudaStream_t st) {
+    // small levels: narrow blocks, so that a few thousand subtrees still spread over many SMs
+    const size_t groups = w_in >> K;
+    const unsigned block = groups >= 148 * 256 ? 256 : (groups >= 148 * 64 ? 128 : 32);
     {
         ProfScope ps(c, st, LEAF ? "merkle_levels_leaf" : "merkle_levels_node");
-        merkle_levels_kernel<K, LEAF><<<grid_for(w_in >> K, 256), 256, 0, st>>>(in, nodes, w_in, c.key);
+        merkle_levels_kernel<K, LEAF><<<grid_for(groups, block), block, 0, st>>>(in, nodes, w_in, c.key);
     }
     HODOR_CUDA_TRY(cudaGetLastError());
     return HODOR_OK;
 }
 
-// Hashes the wide part of the tree.  On return *remaining_width is the width (<= 4096) of the
-// lowest level that has been written; 0 means nothing was done (n <= 4096: the tail kernel takes
-// the leaves directly).
+// Width at which the single-block tail kernel takes over.  The tail is one SM: below this width its
+// cost is the latency of the remaining chain of levels, above it the compression throughput of a
+// single SM (0.19 G/s: 4095 compressions = 22 us) -- so the multi-block kernels go further down than
+// they need to for parallelism's sake.  HODOR_MERKLE_TAIL_MAX overrides (power of two, 2..4096).
+static size_t tail_max() {
+    static size_t v = 0;
+    if (v == 0) {
+        v = 1024;  // measured on the 2^24 FRI chain: 4096 -> 4.45 ms, 1024 -> 4.30, 512 -> 4.30, 256 -> 4.33, 128 -> 4.38
+        if (const char* e = getenv("HODOR_MERKLE_TAIL_MAX")) {
+            const size_t x = (size_t)strtoull(e, nullptr, 10);
+            if (x >= 2 && x <= 4096 && (x & (x - 1)) == 0) v = x;
+        }
+    }
+    return v;
+}
+
+// Hashes the wide part of the tree.  On return *remaining_width is the width (<= tail_max()) of the
+// lowest level that has been written; 0 means nothing was done (n <= tail_max(), or too few leaves
+// for a subtree kernel: the tail kernel takes the leaves directly).
 int merkle_levels(Ctx& c, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st) {
     *remaining_width = 0;
-    if (n <= 4096) return HODOR_OK;
+    const size_t tmax = tail_max();
+    if (n <= tmax || n < 16) return HODOR_OK;
     int rc = launch_levels<3, true>(c, leaves, nodes, n, st);  // levels n/2, n/4, n/8
     if (rc) return rc;
     size_t w = n >> 3;
-    while (w > 4096) {
+    while (w > tmax) {
         int k = 0;
-        while (k < 3 && (w >> (k + 1)) >= 4096) k++;  // land exactly on 4096 or above
+        while (k < 3 && (w >> (k + 1)) >= tmax) k++;  // land exactly on tmax or above
         if (k == 0) k = 1;
         const uint4* in = nodes + 2 * w;
         switch (k) {
