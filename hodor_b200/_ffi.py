@@ -85,6 +85,7 @@ _SIGS = {
     "hodor_cuda_lde": (C.c_int, [u64p, C.c_uint32, C.c_uint32, C.c_int, u64p, C.c_int]),
     "hodor_cuda_lde_batch": (C.c_int, [C.POINTER(u64p), C.POINTER(u64p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "hodor_cuda_elementwise": (C.c_int, [C.c_int, u64p, u64p, u64p, C.c_uint64, C.c_int]),
+    "hodor_cuda_poly_op": (C.c_int, [C.c_int, u64p, u64p, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int]),
     "hodor_cuda_batch_inversion": (C.c_int, [u64p, C.c_uint64, C.c_int]),
     "hodor_cuda_evaluate_at": (C.c_int, [u64p, C.c_uint64, u64p, u64p, C.c_int]),
     "hodor_cuda_merkle_build": (C.c_int, [u64p, C.c_uint64, u8p, C.c_int]),
@@ -108,6 +109,7 @@ _SIGS = {
     "hodor_cuda_lde_cosets_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                             C.c_int, vp]),
     "hodor_cuda_elementwise_dev": (C.c_int, [C.c_int, vp, vp, vp, C.c_uint64, C.c_int, vp]),
+    "hodor_cuda_poly_op_dev": (C.c_int, [C.c_int, vp, vp, u64p, C.c_uint64, vp, C.c_uint64, C.c_int, vp]),
     "hodor_cuda_batch_inversion_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),
     "hodor_cuda_evaluate_at_dev": (C.c_int, [vp, C.c_uint64, u64p, vp, C.c_int, vp]),
     "hodor_cuda_ntt_shard_cols_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_int, vp]),

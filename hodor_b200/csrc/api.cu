@@ -519,7 +519,17 @@ int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d
                                void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
-    return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, pick_stream(c, stream));
+    if (op < 0 || op > 3) return fail(HODOR_ERR_INVALID_ARG, "elementwise: op must be 0..3 (use hodor_cuda_poly_op_dev for the scalar forms)");
+    return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, nullptr, 0, pick_stream(c, stream));
+}
+int hodor_cuda_poly_op_dev(int op, const void* d_a, const void* d_b, const uint64_t scalar[4], uint64_t exp, void* d_out,
+                           uint64_t n, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    Fe s;
+    if (scalar) s = fe_from_u64(scalar);
+    return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, scalar ? &s : nullptr, exp,
+                            pick_stream(c, stream));
 }
 int hodor_cuda_batch_inversion_dev(void* d_a, uint64_t n, int* d_status, int field_id, void* stream) {
     LOCKED_CTX();
@@ -685,22 +695,39 @@ int hodor_cuda_lde_batch(const uint64_t* const* coeffs, uint64_t* const* outs, u
     if (e != cudaSuccess) return cuda_fail(e, "lde_batch");
     return HODOR_OK;
 }
-int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id) {
-    LOCKED_CTX();
-    GET_OPS(field_id);
+static int host_poly_op(Ctx* c, const FieldOps* ops, int op, const uint64_t* a, const uint64_t* b, const uint64_t* scalar,
+                        uint64_t exp, uint64_t* out, uint64_t n) {
     if (n == 0) return HODOR_OK;
-    const size_t nb = op == 3 ? 1 : (size_t)n;
+    if (op < 0 || op >= EW_NUM_OPS) return fail(HODOR_ERR_INVALID_ARG, "unknown elementwise op");
+    const bool needs_b = op <= EW_ADD_SCALED;
+    if (needs_b && b == nullptr) return fail(HODOR_ERR_INVALID_ARG, "elementwise: operand b is NULL");
+    const size_t nb = !needs_b ? 0 : (op == EW_SCALE ? 1 : (size_t)n);
     int rc = c->ensure_io(0, n * 32);
     if (rc) return rc;
-    rc = c->ensure_io(1, nb * 32);
+    rc = c->ensure_io(1, (nb ? nb : 1) * 32);
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], a, n * 32, cudaMemcpyHostToDevice, c->stream));
-    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[1], b, nb * 32, cudaMemcpyHostToDevice, c->stream));
-    rc = ops->elementwise(*c, op, (const uint4*)c->io[0], (const uint4*)c->io[1], (uint4*)c->io[0], n, c->stream);
+    if (nb) HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[1], b, nb * 32, cudaMemcpyHostToDevice, c->stream));
+    Fe s;
+    if (scalar) s = fe_from_u64(scalar);
+    rc = ops->elementwise(*c, op, (const uint4*)c->io[0], (const uint4*)c->io[1], (uint4*)c->io[0], n, scalar ? &s : nullptr,
+                          exp, c->stream);
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[0], n * 32, cudaMemcpyDeviceToHost, c->stream));
     HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return HODOR_OK;
+}
+int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (op < 0 || op > 3) return fail(HODOR_ERR_INVALID_ARG, "elementwise: op must be 0..3 (use hodor_cuda_poly_op for the scalar forms)");
+    return host_poly_op(c, ops, op, a, b, nullptr, 0, out, n);
+}
+int hodor_cuda_poly_op(int op, const uint64_t* a, const uint64_t* b, const uint64_t scalar[4], uint64_t exp, uint64_t* out,
+                       uint64_t n, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return host_poly_op(c, ops, op, a, b, scalar, exp, out, n);
 }
 int hodor_cuda_selftest_mul_pre(int field_id) {
     LOCKED_CTX();

@@ -145,7 +145,8 @@ struct FieldOps {
     int (*ntt)(Ctx&, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_l, const Fe& omega, const Fe* shift0,
                const Fe* step, int out_mode, const Fe* out_g, cudaStream_t st);
     int (*scale_pow)(Ctx&, uint4* a, size_t n, const Fe& g, cudaStream_t st);
-    int (*elementwise)(Ctx&, int op, const uint4* a, const uint4* b, uint4* out, size_t n, cudaStream_t st);
+    int (*elementwise)(Ctx&, int op, const uint4* a, const uint4* b, uint4* out, size_t n, const Fe* scalar, uint64_t exp,
+                       cudaStream_t st);
     int (*batch_inversion)(Ctx&, uint4* a, size_t n, int* d_status, cudaStream_t st);
     int (*evaluate_at)(Ctx&, const uint4* a, size_t n, const Fe& g, uint4* d_out, cudaStream_t st);
     int (*selftest_mul_pre)(Ctx&, unsigned long long* d_mismatch, cudaStream_t st);

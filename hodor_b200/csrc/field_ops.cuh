@@ -538,12 +538,16 @@ struct Ops {
         return HODOR_OK;
     }
 
-    static int elementwise(Ctx& c, int op, const uint4* a, const uint4* b, uint4* out, size_t n, cudaStream_t st) {
-        if (op < 0 || op > 3) return fail(HODOR_ERR_INVALID_ARG, "unknown elementwise op");
+    static int elementwise(Ctx& c, int op, const uint4* a, const uint4* b, uint4* out, size_t n, const Fe* scalar,
+                           uint64_t exp, cudaStream_t st) {
+        if (op < 0 || op >= EW_NUM_OPS) return fail(HODOR_ERR_INVALID_ARG, "unknown elementwise op");
+        const bool needs_b = op <= EW_ADD_SCALED, needs_scalar = op == EW_ADD_SCALED || op == EW_ADD_CONST;
+        if (n && ((needs_b && b == nullptr) || (needs_scalar && scalar == nullptr)))
+            return fail(HODOR_ERR_INVALID_ARG, "elementwise: missing operand for this op");
         const unsigned grid = (unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
         {
             ProfScope ps(c, st, "elementwise");
-            elementwise_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(op, a, b, out, n, 0u);
+            elementwise_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(op, a, b, out, n, scalar ? *scalar : Fld::zero(), exp, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;

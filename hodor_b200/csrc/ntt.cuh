@@ -469,18 +469,40 @@ __global__ void scale_pow_kernel(uint4* a, size_t n, TwoLevel pw, uint32_t zero)
     }
 }
 
-enum : int { EW_MUL = 0, EW_ADD = 1, EW_SUB = 2, EW_SCALE = 3 };
-// elementwise Polynomial ops (src/polynomials/mod.rs:59-83, 744-771, 817-887): out = a (op) b
+enum : int {
+    EW_MUL = 0, EW_ADD = 1, EW_SUB = 2, EW_SCALE = 3,                              // a (op) b; SCALE: b is one element
+    EW_ADD_SCALED = 4, EW_ADD_CONST = 5, EW_NEGATE = 6, EW_SQUARE = 7, EW_POW = 8,  // scalar / exponent forms
+    EW_NUM_OPS = 9
+};
+// elementwise Polynomial ops (src/polynomials/mod.rs:59-83, 640-683, 744-771, 817-887).  `scalar` is a
+// fixed operand for the whole launch (scale, add_assign_scaled), so it goes through mul_pre.
+//   MUL a*b | ADD a+b | SUB a-b | SCALE a*b[0] | ADD_SCALED a + b*scalar | ADD_CONST a + scalar |
+//   NEGATE -a | SQUARE a^2 | POW a^exp
 template <class F>
-__global__ void elementwise_kernel(int op, const uint4* a, const uint4* b, uint4* out, size_t n, uint32_t zero) {
-    const Field<F> fld(threadIdx.x & zero);
+__global__ void elementwise_kernel(int op, const uint4* a, const uint4* b, uint4* out, size_t n,
+                                   const __grid_constant__ Fe scalar, uint64_t exp, uint32_t zero) {
+    const uint32_t oz = threadIdx.x & zero;
+    const Field<F> fld(oz);
+    FePre sp;
+    if (op == EW_SCALE) {
+        fld.make_pre(ld_fe(b, 0), sp.w, sp.q);
+    } else if (op == EW_ADD_SCALED) {
+        fld.make_pre(ld_param(scalar, oz), sp.w, sp.q);
+    }
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
         const Fe x = ld_fe(a, j);
-        const Fe y = ld_fe(b, op == EW_SCALE ? 0 : j);
         Fe r;
-        if (op == EW_MUL || op == EW_SCALE) r = fld.mul(x, y);
-        else if (op == EW_ADD) r = fld.add(x, y);
-        else r = fld.sub(x, y);
+        switch (op) {
+            case EW_MUL: r = fld.mul(x, ld_fe(b, j)); break;
+            case EW_ADD: r = fld.add(x, ld_fe(b, j)); break;
+            case EW_SUB: r = fld.sub(x, ld_fe(b, j)); break;
+            case EW_SCALE: r = mul_by(fld, x, sp); break;
+            case EW_ADD_SCALED: r = fld.add(x, mul_by(fld, ld_fe(b, j), sp)); break;
+            case EW_ADD_CONST: r = fld.add(x, ld_param(scalar, oz)); break;
+            case EW_NEGATE: r = fld.neg(x); break;
+            case EW_SQUARE: r = fld.mul(x, x); break;
+            default: r = fld.pow(x, exp); break;  // EW_POW
+        }
         st_fe(out, j, r);
     }
 }

@@ -180,6 +180,37 @@ class Polynomial:
     def scale(self, worker: Optional[Worker], g) -> None:
         self._ew(3, fld.limbs(g).reshape(1, 4))
 
+    def _op(self, op: int, other=None, scalar=None, exp: int = 0) -> None:
+        ensure_init()
+        n = self.size() if other is None else _as_elems(other).shape[0]
+        assert self.size() >= n
+        b = None if other is None else _p(_as_elems(other))
+        s = None if scalar is None else _p(fld.limbs(scalar))
+        check(lib.hodor_cuda_poly_op(op, _p(self.coeffs), b, s, C.c_uint64(exp), _p(self.coeffs), C.c_uint64(n), self.field_id))
+
+    def add_assign_scaled(self, worker: Optional[Worker], other: "Polynomial", scaling) -> None:
+        """:654-669 / :843-858"""
+        self._op(4, other.coeffs, scaling)
+
+    def add_constant(self, worker: Optional[Worker], constant) -> None:
+        """:831-841"""
+        self._need(VALUES)
+        self._op(5, scalar=constant)
+
+    def negate(self, worker: Optional[Worker] = None) -> None:
+        """:72-83"""
+        self._op(6)
+
+    def square(self, worker: Optional[Worker] = None) -> None:
+        """:760-771"""
+        self._need(VALUES)
+        self._op(7)
+
+    def pow(self, worker: Optional[Worker], exp: int) -> None:
+        """:744-758"""
+        self._need(VALUES)
+        self._op(7 if exp == 2 else 8, exp=exp)
+
     # ---- batch inversion (:889-954) and point evaluation (:685-711) ------------------------------
     def batch_inversion(self, worker: Optional[Worker] = None) -> None:
         """Every value replaced by its inverse; SynthesisError (vector untouched) if one is zero."""

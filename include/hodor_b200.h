@@ -112,6 +112,20 @@ int hodor_cuda_lde_batch(const uint64_t* const* coeffs, uint64_t* const* outs, u
  * 3 scale (b is one element).  out may alias a. */
 int hodor_cuda_elementwise(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int field_id);
 
+/* The remaining elementwise Polynomial methods.  op: 0..3 as above, 4 add_assign_scaled (a + b * scalar,
+ * :654-669, :843-858), 5 add_constant (a + scalar, :831-841), 6 negate (:72-83), 7 square (:760-771),
+ * 8 pow (a^exp, :744-758).  b / scalar may be NULL for the ops that do not use them.  out may alias a. */
+#define HODOR_OP_MUL 0
+#define HODOR_OP_ADD 1
+#define HODOR_OP_SUB 2
+#define HODOR_OP_SCALE 3
+#define HODOR_OP_ADD_SCALED 4
+#define HODOR_OP_ADD_CONST 5
+#define HODOR_OP_NEGATE 6
+#define HODOR_OP_SQUARE 7
+#define HODOR_OP_POW 8
+int hodor_cuda_poly_op(int op, const uint64_t* a, const uint64_t* b, const uint64_t scalar[4], uint64_t exp, uint64_t* out,
+                       uint64_t n, int field_id);
 /* Polynomial<F, Values>::batch_inversion (src/polynomials/mod.rs:889-954): a[i] <- a[i]^-1 in place.
  * A zero element fails with HODOR_ERR_NOT_INVERTIBLE and leaves `a` untouched, like the reference,
  * which returns Err(SynthesisError::Error) before writing anything. */
@@ -167,6 +181,8 @@ int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domai
                             const void* d_challenge, void* d_out, int field_id, void* stream);
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
                                void* stream);
+int hodor_cuda_poly_op_dev(int op, const void* d_a, const void* d_b, const uint64_t scalar[4], uint64_t exp, void* d_out,
+                           uint64_t n, int field_id, void* stream);
 /* d_status: one device int, set to 0 on success and to 1 (vector untouched) when an element is zero */
 int hodor_cuda_batch_inversion_dev(void* d_a, uint64_t n, int* d_status, int field_id, void* stream);
 /* d_out: one element (32 B) on the device */

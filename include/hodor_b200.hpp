@@ -188,6 +188,30 @@ class Polynomial {
         check(hodor_cuda_ifft(raw(), exp, 1, F::ID));
         return Polynomial<F, Coefficients>::adopt(std::move(coeffs_));
     }
+    // ---- elementwise (:59-83, :640-683, :744-771, :817-887) --------------------------------------
+    void scale(const Worker&, const F& g) { op(HODOR_OP_SCALE, g.l, nullptr, 0, size()); }
+    void negate(const Worker&) { op(HODOR_OP_NEGATE, nullptr, nullptr, 0, size()); }
+    void add_assign(const Worker&, const Polynomial& o) { op(HODOR_OP_ADD, o.raw_c(), nullptr, 0, checked(o)); }
+    void sub_assign(const Worker&, const Polynomial& o) { op(HODOR_OP_SUB, o.raw_c(), nullptr, 0, checked(o)); }
+    void add_assign_scaled(const Worker&, const Polynomial& o, const F& s) { op(HODOR_OP_ADD_SCALED, o.raw_c(), s.l, 0, checked(o)); }
+    void mul_assign(const Worker&, const Polynomial& o) {
+        require<Values>();
+        if (o.size() != size()) throw std::logic_error("assert_eq!(self.coeffs.len(), other.coeffs.len())");
+        op(HODOR_OP_MUL, o.raw_c(), nullptr, 0, size());
+    }
+    void add_constant(const Worker&, const F& c) {
+        require<Values>();
+        op(HODOR_OP_ADD_CONST, nullptr, c.l, 0, size());
+    }
+    void square(const Worker&) {
+        require<Values>();
+        op(HODOR_OP_SQUARE, nullptr, nullptr, 0, size());
+    }
+    void pow(const Worker& w, uint64_t exp) {
+        require<Values>();
+        if (exp == 2) return square(w);
+        op(HODOR_OP_POW, nullptr, nullptr, exp, size());
+    }
     void batch_inversion(const Worker&) {  // :889-954; SynthesisError (vector untouched) on a zero value
         require<Values>();
         check(hodor_cuda_batch_inversion(raw(), coeffs_.size(), F::ID));
@@ -215,6 +239,14 @@ class Polynomial {
         minv = F::from_u64(dom.size).inverse().second;
     }
     uint64_t* raw() { return reinterpret_cast<uint64_t*>(coeffs_.data()); }
+    const uint64_t* raw_c() const { return reinterpret_cast<const uint64_t*>(coeffs_.data()); }
+    size_t checked(const Polynomial& o) const {
+        if (size() < o.size()) throw std::logic_error("assert!(self.coeffs.len() >= other.coeffs.len())");
+        return o.size();
+    }
+    void op(int code, const uint64_t* b, const uint64_t* scalar, uint64_t exp, size_t n) {
+        check(hodor_cuda_poly_op(code, raw(), b, scalar, exp, raw(), n, F::ID));
+    }
     template <class Need>
     void require() const {
         static_assert(std::is_same<Form, Need>::value, "wrong polynomial form for this transform");

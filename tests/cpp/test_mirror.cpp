@@ -76,6 +76,35 @@ static void test_batch_inversion_and_evaluate() {
     }
     CHECK(threw);
     CHECK(bad.as_ref() == with_zero);
+    // elementwise ops against scalar field arithmetic
+    {
+        const auto b = random_vec<F>(1 << 10, 42);
+        auto x = Polynomial<F, Values>::from_values(a);
+        const auto y = Polynomial<F, Values>::from_values(b);
+        x.add_assign_scaled(worker, y, a[3]);   // a + b * s
+        x.add_constant(worker, b[7]);           // + c
+        x.negate(worker);
+        x.square(worker);
+        x.pow(worker, 5);
+        x.scale(worker, a[9]);
+        x.mul_assign(worker, y);
+        x.sub_assign(worker, y);
+        for (size_t i = 0; i < a.size(); i += 131) {
+            F t = b[i];
+            t.mul_assign(a[3]);
+            F e = a[i];
+            e.add_assign(t);
+            e.add_assign(b[7]);
+            F neg = F::zero();
+            neg.sub_assign(e);
+            neg.square();
+            F r = neg.pow(5);
+            r.mul_assign(a[9]);
+            r.mul_assign(b[i]);
+            r.sub_assign(b[i]);
+            CHECK(x.as_ref()[i] == r);
+        }
+    }
     const auto coeffs = Polynomial<F, Coefficients>::from_coeffs(a);
     const F z = a[5];
     F expect;

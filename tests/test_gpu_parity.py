@@ -48,6 +48,34 @@ def test_elementwise_field_ops(hodor, oracle, fid):
 
 
 @pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_polynomial_scalar_ops(hodor, oracle, fid):
+    """negate, add_constant, add_assign_scaled, square, pow (src/polynomials/mod.rs:72-83, 654-669,
+    744-771, 831-858) against the oracle's scalar field arithmetic."""
+    n = 1 << 10
+    a, b = oracle.random_elements(fid, n, 11), oracle.random_elements(fid, n, 12)
+    c = oracle.field_constants(fid)
+    p = oracle.limbs_to_int(c["p"])
+    a[:4] = oracle.ints_to_array([0, 1, p - 1, oracle.limbs_to_int(c["r"])])
+    s = b[5]
+    W = hodor.Worker()
+    x = hodor.Polynomial.from_values(fid, a); x.negate(W)
+    assert np.array_equal(x.as_ref(), oracle.sub(fid, np.zeros_like(a), a))
+    x = hodor.Polynomial.from_values(fid, a); x.add_constant(W, s)
+    assert np.array_equal(x.as_ref(), oracle.add(fid, a, np.tile(s, (n, 1))))
+    x = hodor.Polynomial.from_values(fid, a); x.add_assign_scaled(W, hodor.Polynomial.from_values(fid, b), s)
+    assert np.array_equal(x.as_ref(), oracle.add(fid, a, oracle.mul(fid, b, np.tile(s, (n, 1)))))
+    x = hodor.Polynomial.from_values(fid, a); x.square(W)
+    assert np.array_equal(x.as_ref(), oracle.mul(fid, a, a))
+    x = hodor.Polynomial.from_values(fid, a); x.pow(W, 2)
+    assert np.array_equal(x.as_ref(), oracle.mul(fid, a, a))
+    for e in (0, 1, 3, 65537, (1 << 64) - 1):
+        x = hodor.Polynomial.from_values(fid, a[:64]); x.pow(W, e)
+        assert np.array_equal(x.as_ref(), np.stack([oracle.pow_(fid, v, e) for v in a[:64]])), e
+    x = hodor.Polynomial.from_values(fid, a); x.scale(W, s)
+    assert np.array_equal(x.as_ref(), oracle.mul(fid, a, np.tile(s, (n, 1))))
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
 def test_fixed_operand_multiplier_selftest(hodor, fid):
     """Field::mul_pre (the multiplier of every table multiply) against the Montgomery multiplier on
     the device, including with the guard threshold forced low so that the out-of-line carry fix-up
