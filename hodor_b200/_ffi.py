@@ -103,6 +103,7 @@ _SIGS = {
     "hodor_cuda_ifft_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_int, vp]),
     "hodor_cuda_lde_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_int, vp]),
     "hodor_cuda_merkle_build_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.c_int, vp]),
+    "hodor_cuda_merkle_top_dev": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, vp]),
     "hodor_cuda_fri_fold_dev": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, C.c_int, vp]),
     "hodor_cuda_fri_fold_shard_dev": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp,
                                                 C.c_int, vp]),

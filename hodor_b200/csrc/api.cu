@@ -474,6 +474,13 @@ int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes,
     return do_merkle(*c, ops, (const uint4*)d_leaves, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,
                      pick_stream(c, stream));
 }
+int hodor_cuda_merkle_top_dev(void* d_nodes, uint64_t w, void* d_root, void* d_challenge, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (!is_pow2(w) || w > 4096) return fail(HODOR_ERR_INVALID_ARG, "merkle_top: width must be a power of two <= 4096");
+    return ops->merkle_tail(*c, (const uint4*)d_nodes, (uint4*)d_nodes, (uint32_t)w, false, (uint4*)d_root, (uint4*)d_challenge,
+                            pick_stream(c, stream));
+}
 int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
                             const void* d_challenge, void* d_out, int field_id, void* stream) {
     LOCKED_CTX();

