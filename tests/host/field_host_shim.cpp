@@ -16,6 +16,22 @@ static void run(int op, const Fe* a, const Fe* b, Fe* out, size_t n) {
             case 4: out[i] = f.to_mont(a[i]); break;
             case 5: out[i] = f.from_mont(a[i]); break;
             case 6: out[i] = f.neg(a[i]); break;
+            case 7: {  // fixed-operand multiplier: a * b with b converted to (w, floor(w * 2^256 / p))
+                Fe w, q;
+                f.make_pre(b[i], w, q);
+                out[i] = f.mul_pre(a[i], w, q);
+                break;
+            }
+            case 8: {  // the quotient word table itself: out = q of make_pre(b)
+                Fe w;
+                f.make_pre(b[i], w, out[i]);
+                break;
+            }
+            case 9: {  // pre_dropped_carry(a, b) in word 0
+                out[i] = Field<F>::zero();
+                out[i].v[0] = Field<F>::pre_dropped_carry(a[i].v, b[i].v);
+                break;
+            }
         }
     }
 }

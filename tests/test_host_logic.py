@@ -129,6 +129,68 @@ def test_device_multiplier_algorithm_on_host(oracle, pymodel, host_field_shim, f
     assert oracle.array_to_ints(run(6)) == [(-x) % F.p for x in ai]
 
 
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_fixed_operand_multiplier_on_host(oracle, pymodel, host_field_shim, fid):
+    """Field::mul_pre / make_pre (csrc/field.cuh, host build): same bits as the Montgomery product, the
+    table quotient is floor(w * 2^256 / p), and the out-of-line carry helper equals the dropped part of
+    the truncated high product (model of the device code path: tools/gen_shoup.py)."""
+    F = getattr(pymodel, {0: "BLS12_381_FR", 1: "BN254_FR", 2: "STARK252"}[fid])
+    n = 4000
+    a, b = oracle.random_elements(fid, n, 3), oracle.random_elements(fid, n, 4)
+    edge = oracle.ints_to_array([0, 1, F.p - 1, F.R, F.p - 2, 2, (F.p - 1) // 2, (F.p + 1) // 2])
+    a[:8], b[:8] = edge, edge[::-1]
+    a[8:16], b[8:16] = edge, edge
+    a[16:24], b[16:24] = edge, oracle.ints_to_array([F.p - 1] * 8)
+    out = np.zeros_like(a)
+
+    def run(op, x=a, y=b):
+        rc = host_field_shim.host_field_op(fid, op, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                           out.ctypes.data_as(C.c_void_p), C.c_size_t(len(x)))
+        assert rc == 0
+        return out.copy()
+
+    assert np.array_equal(run(7), oracle.mul(fid, a, b))
+    plain = [F.from_mont(x) for x in oracle.array_to_ints(b)]
+    assert oracle.array_to_ints(run(8)) == [(w << 256) // F.p for w in plain]
+    # truncated high product: kept = words >= 7 (+ high words of column 6); dropped part D < 14 * 2^224 and
+    # pre_dropped_carry == D >> 224, for arbitrary 256-bit operands (not only field elements)
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    y = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    x[:3] = y[:3] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    x[3:6, :3] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    got = run(9, x, y)[:, 0] & np.uint64(0xFFFFFFFF)
+    M = (1 << 32) - 1
+    for k in range(n):
+        A, B = oracle.limbs_to_int(x[k]), oracle.limbs_to_int(y[k])
+        aw = [(A >> (32 * i)) & M for i in range(8)]
+        bw = [(B >> (32 * i)) & M for i in range(8)]
+        kept = 0
+        for i in range(8):
+            for j in range(8):
+                c, pr = i + j, aw[i] * bw[j]
+                if c >= 7:
+                    kept += pr << (32 * c)
+                elif c == 6:
+                    kept += (pr >> 32) << (32 * 7)
+        D = A * B - kept
+        assert 0 <= D < 14 << 224
+        assert int(got[k]) == D >> 224
+        guard, q = (kept >> 224) & M, kept >> 256
+        assert q + ((guard + (D >> 224)) >> 32) == (A * B) >> 256
+        if guard < 0xFFFFFFF2:
+            assert q == (A * B) >> 256  # the fast path needs no fix-up
+
+
+def test_generated_carry_chains_are_in_sync():
+    """csrc/shoup_rows.cuh is generated: the committed file must be what tools/gen_shoup.py emits."""
+    import subprocess
+    import sys
+    want = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_shoup.py")], capture_output=True, text=True,
+                          check=True, env={k: v for k, v in os.environ.items() if k not in ("IMM_ROLE", "IMM_FIRST", "SWAP_HI")}).stdout
+    assert open(os.path.join(ROOT, "hodor_b200", "csrc", "shoup_rows.cuh")).read() == want
+
+
 def test_no_gpu_means_loud_failure_not_cpu_compute():
     """Only meaningful where no GPU is visible (the build container): the product must refuse."""
     import hodor_b200 as H
