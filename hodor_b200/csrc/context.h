@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -39,12 +40,14 @@ struct PowTables {
     uint32_t stride_hi() const { return 1u << hi_bits; }
 };
 
+constexpr uint32_t FLAT_MAX_LOG = 21;  // largest sub-transform that gets a flat inter-pass twiddle table (128 MiB)
+
 struct NttTables {
     PowTables pw;            // powers of omega, exponents [0, 2^log_n)
     // tw_b and tw_direct entries are FePre (64 B): read directly as multipliers
     uint4* tw_b[10] = {};    // tw_b[B][x] = omega^(x << (log_n - B)), B in 6..9 (as used by the plan)
     uint4* tw_b_block = nullptr;
-    uint4* tw_direct[17] = {};  // tw_direct[k][x] = omega^(x << (log_n - k)), x < 2^k: flat inter-pass twiddles, k <= 16
+    uint4* tw_direct[FLAT_MAX_LOG + 1] = {};  // tw_direct[k][x] = omega^(x << (log_n - k)), x < 2^k: flat inter-pass twiddles
     uint4* tw_direct_block = nullptr;
     FePre wr[7];             // omega_16^k, k = 1..7, fixed-operand form
     size_t bytes = 0;
@@ -116,10 +119,26 @@ struct NttPlan {
     int passes = 0;  // 0 => single-block kernel
     int b[4] = {0, 0, 0, 0};
 };
+// Digits are balanced in 6..max_digit.  max_digit = 9 gives the fewest passes over HBM, max_digit = 8
+// avoids the 512-point tiles (128 KiB of shared memory: one resident block per SM, radix-8 groups at
+// 124 registers), at the price of a fourth pass for 2^25..2^27.  HODOR_NTT_MAX_DIGIT overrides.
+inline int ntt_max_digit() {
+    static int v = 0;
+    if (v == 0) {
+        v = 8;
+        if (const char* e = getenv("HODOR_NTT_MAX_DIGIT")) {
+            const int x = atoi(e);
+            if (x == 8 || x == 9) v = x;
+        }
+    }
+    return v;
+}
 inline NttPlan make_plan(uint32_t log_n) {
     NttPlan p;
     if (log_n <= 11) return p;
-    p.passes = (int)((log_n + 8) / 9);
+    const int md = ntt_max_digit();
+    p.passes = (int)((log_n + md - 1) / md);
+    if ((int)log_n / p.passes < 6 && p.passes > 2) p.passes--;  // digits below 6 are not built: fewer, wider passes
     const int base = (int)log_n / p.passes, rem = (int)log_n % p.passes;
     for (int i = 0; i < p.passes; i++) p.b[i] = base + (i < rem ? 1 : 0);
     return p;

@@ -236,13 +236,15 @@ struct Ops {
                 HODOR_CUDA_TRY(cudaGetLastError());
                 HODOR_CUDA_TRY(cudaStreamSynchronize(st));
                 // flat inter-pass twiddle tables for every non-last pass whose sub-transform N = 2^(s+B)
-                // is at most 2^16 (for 2^24 = 8+8+8 that is pass 2: 65536 entries, 2 MiB)
+                // is at most 2^FLAT_MAX_LOG (for 2^24 = 8+8+8 that is pass 2: 65536 entries, 4 MiB; for the
+                // four-pass plans of 2^25..2^28 pass 2 has N = 2^18..2^21, up to 128 MiB).  Pass 1 of a
+                // transform >= 2^20 uses the expanded per-element table instead.
                 size_t dtotal = 0;
                 uint32_t below = log_n;
                 for (int i = 0; i + 1 < plan.passes; i++) {
                     const uint32_t k = below;  // s + B of pass i
                     below -= plan.b[i];
-                    if (k <= 16 && t.tw_direct[k] == nullptr) {
+                    if (k <= FLAT_MAX_LOG && !(i == 0 && log_n >= 20) && t.tw_direct[k] == nullptr) {
                         t.tw_direct[k] = (uint4*)1;  // mark
                         dtotal += (size_t)1 << k;
                     }
@@ -250,7 +252,7 @@ struct Ops {
                 if (dtotal) {
                     HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_direct_block, dtotal * sizeof(FePre)));
                     uint4* dcur = t.tw_direct_block;
-                    for (uint32_t k = 0; k <= 16; k++) {
+                    for (uint32_t k = 0; k <= FLAT_MAX_LOG; k++) {
                         if (t.tw_direct[k] == nullptr) continue;
                         const Fe base = pow2k(omega, log_n - k);
                         HODOR_CUDA_TRY(cudaMemcpyAsync(d_base, &base, sizeof(Fe), cudaMemcpyHostToDevice, st));
@@ -498,7 +500,7 @@ struct Ops {
             p.s = below;
             p.tw_b = tw->tw_b[b];
             p.tw_full = (i == 0 && !last) ? tw_full : nullptr;
-            p.tw_direct = (!last && below + b <= 16) ? tw->tw_direct[below + b] : nullptr;
+            p.tw_direct = (!last && below + b <= FLAT_MAX_LOG) ? tw->tw_direct[below + b] : nullptr;
             p.tw_shift = log_n - below - b;
             p.flags = last ? flags : 0;
             if (!last) {

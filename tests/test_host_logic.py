@@ -209,9 +209,13 @@ def test_no_gpu_means_loud_failure_not_cpu_compute():
 
 
 def test_plan_covers_all_sizes():
-    """The pass plan used by csrc (context.h make_plan), restated: digits in 6..9 summing to log_n."""
-    for ln in range(12, 33):
-        passes = (ln + 8) // 9
-        base, rem = divmod(ln, passes)
-        digits = [base + (1 if i < rem else 0) for i in range(passes)]
-        assert sum(digits) == ln and all(6 <= d <= 9 for d in digits) and passes <= 4
+    """The pass plan used by csrc (context.h make_plan), restated: digits in 6..9 summing to log_n, at
+    most four passes, for both plan policies (HODOR_NTT_MAX_DIGIT = 8 default, 9)."""
+    for md in (8, 9):
+        for ln in range(12, 33):
+            passes = (ln + md - 1) // md
+            if ln // passes < 6 and passes > 2:
+                passes -= 1
+            base, rem = divmod(ln, passes)
+            digits = [base + (1 if i < rem else 0) for i in range(passes)]
+            assert sum(digits) == ln and all(6 <= d <= 9 for d in digits) and passes <= 4, (md, ln, digits)
