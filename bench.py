@@ -38,6 +38,8 @@ LOG_L = 3
 FRI_LOG_N = 24
 FRI_L = 8
 FRI_OUT = 1
+WORKLOAD = (f"coset LDE 2^{LOG_N} -> 2^{LOG_N + LOG_L} (blowup {1 << LOG_L}: {1 << LOG_L} coset NTTs of 2^{LOG_N}) over "
+            "bn256.rs Fr (= BLS12-381 Fr), natural order in/out; per GPU")
 P_TOP_LIMB = 0x73EDA753299D7D48  # top u64 limb of the modulus: any element with a smaller top limb is canonical
 
 
@@ -176,8 +178,9 @@ def run_reference(args, rank: int):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery)",
         "data": "synthetic",
-        "config": {"workload": f"coset LDE 2^{LOG_N} x{1 << LOG_L} over bn256.rs Fr (BLS12-381 Fr), CPU sample 2^{sample_log_n}",
-                   "field": "bls12_381_fr", "reference_impl": "C restatement of hodor's crossbeam path (Rust toolchain unavailable)"},
+        "config": {"workload": WORKLOAD, "field": "bls12_381_fr", "log_n": LOG_N, "lde_factor": 1 << LOG_L,
+                   "sample": f"each timed step is the same transform at 2^{sample_log_n} (1/16 of the workload) on the host cores",
+                   "reference_impl": "C restatement of hodor's crossbeam path (Rust toolchain unavailable)"},
         "cpu_baseline": {"value": value, "unit": "field-elems/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "field-elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fri": {"metric": "fri_merkle_leaves_per_sec", "value": fri_value, "unit": "leaves/s",
@@ -496,8 +499,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8 x u32 Montgomery limbs, INT32 pipe)",
             "data": "synthetic",
-            "config": {"workload": f"coset LDE 2^{LOG_N} -> 2^{LOG_N + LOG_L} (blowup {L}: {L} coset NTTs of 2^{LOG_N}) over "
-                                   "bn256.rs Fr (= BLS12-381 Fr), natural order in/out; per GPU",
+            "config": {"workload": WORKLOAD,
                        "field": "bls12_381_fr", "log_n": LOG_N, "lde_factor": L, "passes": 3,
                        "l2_policy": "inputs (512 MiB) and outputs (4 GiB) exceed the 126 MB L2; no flush between steps",
                        "parallelism": f"{world} independent polynomials, one per GPU" if world > 1 else "single GPU"},
