@@ -175,10 +175,13 @@ DEV void dif_inreg(const Field<F>& fld, Fe (&x)[1 << LOGR], const NttPass& p, ui
 #ifndef HODOR_RADIX4_GROUPS
 #define HODOR_RADIX4_GROUPS 1
 #endif
+#ifndef HODOR_B6_RADIX4
+#define HODOR_B6_RADIX4 0  // B = 6 as 2+2+2 (2.25 multiplies per element, 12 blocks/SM) instead of 3+3 (2.125, 8 blocks/SM)
+#endif
 template <int B>
 struct Groups {
-    static constexpr bool RADIX4 = HODOR_RADIX4_GROUPS && (B == 7 || B == 8);
-    static constexpr int R1 = RADIX4 ? (B == 8 ? 2 : 1) : 3;
+    static constexpr bool RADIX4 = HODOR_RADIX4_GROUPS && (B == 7 || B == 8 || (HODOR_B6_RADIX4 && B == 6));
+    static constexpr int R1 = RADIX4 ? (B == 7 ? 1 : 2) : 3;
     static constexpr int REM = B - 3;
     static constexpr int R2 = RADIX4 ? 2 : (REM <= 3 ? REM : (REM + 1) / 2);
     static constexpr int R3 = RADIX4 ? 2 : REM - R2;
@@ -198,7 +201,7 @@ struct PassOccupancy {
     static constexpr int EPT = (HODOR_B8_EPT4 && B == 8 && Groups<8>::RADIX4) ? 4 : 8;
     static constexpr int THREADS = (8 << B) / EPT;
     static constexpr int MIN_BLOCKS =
-        B >= 9 ? 1 : (B == 8 ? (EPT == 4 ? 2 : (Groups<8>::RADIX4 ? 3 : 2)) : (B == 7 ? (Groups<7>::RADIX4 ? 6 : 4) : 8));
+        B >= 9 ? 1 : (B == 8 ? (EPT == 4 ? 2 : (Groups<8>::RADIX4 ? 3 : 2)) : (B == 7 ? (Groups<7>::RADIX4 ? 6 : 4) : (Groups<6>::RADIX4 ? 12 : 8)));
 };
 
 // One group of the block-local NTT: every thread owns 8 elements = 8 >> LOGR butterflies of radix
@@ -211,6 +214,14 @@ struct PassOccupancy {
 // selected constants) are unrolled; every per-element table multiply -- coset scaling on load,
 // inter-group twiddle, inter-pass twiddle on store -- runs in a rolled loop over the thread's own
 // slots of the shared tile (owner-only accesses: no barrier needed), one multiplier body each.
+#ifndef HODOR_ROLL_UNROLL
+#define HODOR_ROLL_UNROLL 1  // table-multiply loops: 1 = fully rolled; 2 = two multiplies in flight per thread
+#endif
+#if HODOR_ROLL_UNROLL == 2
+#define HODOR_ROLLED _Pragma("unroll 2")
+#else
+#define HODOR_ROLLED _Pragma("unroll 1")
+#endif
 template <class F, int B, int LOGR, int SL, int TWSH, bool FROM_GLOBAL, bool MUL_ON_LOAD, bool TO_GLOBAL, class LoadG,
           class StoreG>
 DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t tid, uint32_t oz, LoadG&& load_global,
@@ -231,7 +242,7 @@ DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t ti
         const uint32_t slot0 = base * 8 + c;
         Fe x[R];
         if constexpr (FROM_GLOBAL && MUL_ON_LOAD) {
-#pragma unroll 1
+HODOR_ROLLED
             for (uint32_t d = 0; d < (uint32_t)R; d++) sts_fe(sm, PLANE, slot0 + d * STEP, load_global(base + (d << SL), c));
         }
 #pragma unroll
@@ -243,7 +254,7 @@ DEV void ntt_group(const Field<F>& fld, const NttPass& p, uint4* sm, uint32_t ti
 #pragma unroll
         for (int k = 0; k < R; k++) sts_fe(sm, PLANE, slot0 + k * STEP, x[bitrev_c(k, LOGR)]);
         if constexpr (SL > 0 || TO_GLOBAL) {
-#pragma unroll 1
+HODOR_ROLLED
             for (uint32_t k = TO_GLOBAL ? 0u : 1u; k < (uint32_t)R; k++) {
                 Fe v = lds_fe(sm, PLANE, slot0 + k * STEP);
                 if constexpr (SL > 0) {
