@@ -309,6 +309,29 @@ def test_lde_2p24_x8_properties(hodor, oracle, pymodel):
     assert np.array_equal(back, a)
 
 
+def test_four_pass_plan_2p25(hodor, oracle):
+    """Transforms of 2^25 and up run FOUR passes over HBM (2^25 = 7+6+6+6: two middle digits in the
+    last pass's output index).  Checked against an independent code path, the reference's own identity
+    (test_lde_correctness, src/polynomials/mod.rs:988-1034): the NTT of a zero-padded vector equals the
+    multi-coset LDE -- which for 2^24 x 2 runs the three-pass plan per coset -- and by round trips of
+    the plain and coset transforms (input scaling and output scaling on the four-pass path)."""
+    fid, log_n = 0, 25
+    n = 1 << log_n
+    a = oracle.random_elements(fid, n // 2, seed=25)
+    lde = hodor.Polynomial.from_coeffs(fid, a).lde(hodor.Worker(), 2).as_ref()
+    padded = np.zeros((n, 4), np.uint64)
+    padded[: n // 2] = a
+    full = hodor.Polynomial.from_coeffs(fid, padded).fft(hodor.Worker())
+    assert np.array_equal(full.as_ref(), lde)
+    back = full.ifft(hodor.Worker())
+    assert np.array_equal(back.as_ref(), padded)
+    del lde, full
+    x = oracle.random_elements(fid, n, seed=26)
+    y = hodor.Polynomial.from_coeffs(fid, x).coset_fft(hodor.Worker())
+    assert not np.array_equal(y.as_ref()[:1024], x[:1024])
+    assert np.array_equal(y.icoset_fft(hodor.Worker()).as_ref(), x)
+
+
 # ----------------------------------------------------------------------------------------------
 # Merkle oracle
 # ----------------------------------------------------------------------------------------------
