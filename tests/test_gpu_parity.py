@@ -552,6 +552,30 @@ def test_sharded_steps_single_gpu(hodor, oracle, world):
     assert np.array_equal(gather_output(outs), oracle.serial_fft(fid, a, omega, log_n))
 
 
+def test_sharded_steps_large_local_transform(hodor, oracle):
+    """Same emulation at 2^26 over 2 ranks: each rank's column step is a 2^25-point transform, i.e. the
+    four-pass plan with the per-rank output scaling fused into its last pass; checked against the direct
+    single-GPU NTT of the whole vector."""
+    import torch
+    from hodor_b200 import device as dev
+    from hodor_b200.sharded import CudaBackend, gather_output, scatter_input
+    fid, log_n, world = 0, 26, 2
+    log_g = 1
+    a = oracle.random_elements(fid, 1 << log_n, seed=56)
+    omega = oracle.domain_generator(fid, log_n)
+    be = CudaBackend()
+    cols = [be.shard_cols(dev.to_device(scatter_input(a, world, g)), log_n, log_g, g, omega, fid) for g in range(world)]
+    m = (1 << log_n) // world
+    chunk = m // world
+    outs = []
+    for h in range(world):
+        recv = torch.cat([cols[g][h * chunk : (h + 1) * chunk] for g in range(world)]).contiguous()
+        outs.append(dev.to_host(be.shard_rows(recv, log_n, log_g, h, omega, fid)))
+    del cols
+    want = hodor.Polynomial.from_coeffs(fid, a).fft(hodor.Worker()).as_ref()
+    assert np.array_equal(gather_output(outs), want)
+
+
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_sharded_lde_fri_building_blocks(hodor, oracle, world):
     """hodor_cuda_lde_cosets_dev / hodor_cuda_fri_fold_shard_dev for every rank of a `world`-GPU box,
