@@ -138,6 +138,47 @@ def test_evaluate_at_matches_oracle(hodor, oracle, fid):
         assert np.array_equal(poly.evaluate_at(hodor.Worker(), x), lde.as_ref()[idx])
 
 
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_device_polynomial_matches_host_polynomial(hodor, oracle, fid):
+    """DevicePolynomial (vector resident in HBM, `_dev` entry points) gives the bits of the
+    host-pointer Polynomial on a chain shaped like the ALI / DEEP steps: LDE, elementwise forms, batch
+    inversion, transforms back, point evaluation."""
+    from hodor_b200 import _ffi
+    from hodor_b200.device import DevicePolynomial
+
+    W = hodor.Worker()
+    a, b = oracle.random_elements(fid, 1 << 11, seed=81), oracle.random_elements(fid, 1 << 11, seed=82)
+    s, z = b[3], a[7]
+
+    def chain(P):
+        x = P.from_coeffs(fid, a).coset_lde(W, 4)
+        y = P.from_coeffs(fid, b).coset_lde(W, 4)
+        x.add_assign_scaled(W, y, s)
+        x.add_constant(W, s)
+        x.square(W)
+        x.pow(W, 3)
+        x.negate(W)
+        x.batch_inversion(W)
+        x.mul_assign(W, y)
+        x.sub_assign(W, y)
+        x.scale(W, z)
+        x.add_assign(W, y)
+        c = x.icoset_fft(W)
+        return c, c.evaluate_at(W, z)
+
+    hc, hv = chain(hodor.Polynomial)
+    dc, dv = chain(DevicePolynomial)
+    assert np.array_equal(dc.to_host(), hc.as_ref()) and np.array_equal(dv, hv)
+    back = dc.clone().fft(W).ifft(W)
+    assert np.array_equal(back.to_host(), hc.as_ref())
+    bad = a.copy()
+    bad[100] = 0
+    dz = DevicePolynomial.from_values(fid, bad)
+    with pytest.raises(_ffi.SynthesisError):
+        dz.batch_inversion(W)
+    assert np.array_equal(dz.to_host(), bad)
+
+
 def test_batch_inversion_2p24_properties(hodor, oracle):
     """BASELINE-size check without a 2^24 CPU pass: a * a^-1 == 1 everywhere, and inverting twice
     returns the input."""
