@@ -60,6 +60,16 @@ def main():
                                  "final_root": pr.final_root.hex(),
                                  "final_coefficients": [hex(F.to_mont(c)) for c in pr.final_coefficients],
                                  "values_sha256": [digest(mont_bytes(F, v)) for v in pr.layer_values]})
+        # Polynomial::batch_inversion / evaluate_at (src/polynomials/mod.rs:889-954, 685-711)
+        for ci, ln in enumerate([0, 3, 8, 12]):
+            seed = 0x4000 + ci
+            a = [F.from_mont(x) for x in M.random_mont_elements(F, 1 << ln, seed)]
+            inv = [pow(v, -1, F.p) for v in a]
+            out["cases"].append({"kind": "batch_inversion", "field": fid, "log_n": ln, "seed": seed,
+                                 "sha256": digest(mont_bytes(F, inv)), "first": hex(F.to_mont(inv[0]))})
+            z = F.from_mont(M.random_mont_elements(F, 1, seed + 0x100)[0])
+            out["cases"].append({"kind": "evaluate_at", "field": fid, "log_n": ln, "seed": seed, "point_seed": seed + 0x100,
+                                 "value": hex(F.to_mont(M.evaluate(F, a, z)))})
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

@@ -42,6 +42,12 @@ class OracleImpl:
         p = self.O.fri_commit(fid, a, L, oc)
         return p.roots(), p.challenges, p.final_root, p.final_coefficients, p.layer_values
 
+    def batch_inversion(self, fid, a):
+        return self.O.batch_inversion(fid, a)
+
+    def evaluate_at(self, fid, a, z):
+        return self.O.evaluate_at(fid, a, z)
+
 
 class CudaImpl:
     def __init__(self, H):
@@ -62,6 +68,14 @@ class CudaImpl:
         p = self.H.NaiveFriIop.proof_from_lde(self.H.Polynomial.from_values(fid, a), L, oc, None)
         return p.get_roots(), p.challenges, p.get_final_root(), p.final_coefficients, [v.as_ref() for v in p.intermediate_values]
 
+    def batch_inversion(self, fid, a):
+        p = self.H.Polynomial.from_values(fid, a)
+        p.batch_inversion(None)
+        return p.as_ref()
+
+    def evaluate_at(self, fid, a, z):
+        return self.H.Polynomial.from_coeffs(fid, a).evaluate_at(None, z)
+
 
 def check_case(impl, O, c):
     fid, ln = c["field"], c["log_n"]
@@ -77,6 +91,12 @@ def check_case(impl, O, c):
         assert nodes[1].tobytes().hex() == c["root"]
         assert sha(nodes) == c["nodes_sha256"]
         assert np.array_equal(chal, hexint(c["challenge"]))
+    elif c["kind"] == "batch_inversion":
+        r = impl.batch_inversion(fid, a)
+        assert sha(r) == c["sha256"] and np.array_equal(r[0], hexint(c["first"]))
+    elif c["kind"] == "evaluate_at":
+        z = O.random_elements(fid, 1, c["point_seed"])[0]
+        assert np.array_equal(impl.evaluate_at(fid, a, z), hexint(c["value"]))
     elif c["kind"] == "fri":
         roots, chal, final_root, final_coeffs, values = impl.fri(fid, a, c["lde_factor"], c["out_coeffs"])
         assert [bytes(r).hex() for r in roots] == c["roots"]
