@@ -219,3 +219,53 @@ def test_plan_covers_all_sizes():
             base, rem = divmod(ln, passes)
             digits = [base + (1 if i < rem else 0) for i in range(passes)]
             assert sum(digits) == ln and all(6 <= d <= 9 for d in digits) and passes <= 4, (md, ln, digits)
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_fri_verify_proof_on_oracle_built_proofs(oracle, fid):
+    """NaiveFriIop.verify_proof (src/fri/verifier.rs:130-290, host-side scalar work through the
+    library's hodor_field_* helpers) accepts proofs assembled from the oracle's commit chain of a
+    low-degree LDE -- queries laid out as produce_proof does (src/fri/query_producer.rs:10-53) -- and
+    rejects a wrong claimed value, a tampered leaf, a tampered path and a wrong final coefficient."""
+    from hodor_b200.domains import Domain
+    from hodor_b200.fri import FRIProof, NaiveFriIop
+    from hodor_b200.iop import TrivialBlake2sIopQuery, TrivialCombiner
+
+    log_n, L, out_coeffs = 5, 4, 1  # the reference's own shape (src/fri/mod.rs:436): one final coefficient, odd query index
+    coeffs = oracle.random_elements(fid, 1 << log_n, seed=77)
+    lde = oracle.lde(fid, coeffs, log_n, L, True)
+    proto = oracle.fri_commit(fid, lde, L, out_coeffs)
+    layers = [(proto.l0_nodes, lde)] + list(zip(proto.layer_nodes, proto.layer_values))
+
+    def make_proof(index):
+        queries, roots = [], []
+        size, idx = lde.shape[0], index
+        for nodes, values in layers:
+            for c in TrivialCombiner.get_coset_for_natural_index(idx, size):
+                queries.append(TrivialBlake2sIopQuery(c, values[c].copy(), oracle.merkle_path(fid, nodes, values, c)))
+            roots.append(nodes[1].tobytes())
+            idx, size = Domain.index_and_size_for_next_domain(idx, size)
+        return FRIProof(queries, roots, proto.final_coefficients.copy(), 1 << log_n, out_coeffs, L, fid)
+
+    # the reference's domain check (verifier.rs:147-157) only lets odd indices through:
+    # (w^idx)^(N/2) == 1 for every even idx is reported as "not in the LDE domain"
+    from hodor_b200._ffi import SynthesisError
+    for index in (0, 2, 36):
+        with pytest.raises(SynthesisError):
+            NaiveFriIop.verify_proof(make_proof(index), index, lde[index])
+    for index in (1, 37, lde.shape[0] // 2 + 5, lde.shape[0] - 1):
+        proof = make_proof(index)
+        assert len(proof.roots) == len(layers) and len(proof.queries) == 2 * len(layers)
+        assert NaiveFriIop.verify_proof(proof, index, lde[index]) is True
+        assert NaiveFriIop.verify_proof(proof, index, lde[(index + 1) % lde.shape[0]]) is False
+    index = 37
+    bad = make_proof(index)
+    bad.queries[2]._value = bad.queries[2]._value.copy()
+    bad.queries[2]._value[0] ^= np.uint64(1)
+    assert NaiveFriIop.verify_proof(bad, index, lde[index]) is False
+    bad = make_proof(index)
+    bad.queries[1]._path = [bytes(32)] + bad.queries[1]._path[1:]
+    assert NaiveFriIop.verify_proof(bad, index, lde[index]) is False
+    bad = make_proof(index)
+    bad.final_coefficients[0, 0] ^= np.uint64(1)
+    assert NaiveFriIop.verify_proof(bad, index, lde[index]) is False
