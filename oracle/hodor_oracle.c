@@ -580,6 +580,87 @@ API int oracle_serial_fft_radix_4(int field, uint64_t *a, const uint64_t *omega,
     if (log_n % 2) return -2; /* assert!(log_n % 2 == 0) */
     serial_fft_radix_4(F, (fe *)a, (const fe *)omega, log_n); return 0;
 }
+/* serial_DIT_fft (src/fft/dit_fft/mod.rs:4-53): decimation-in-frequency butterflies with a running
+ * twiddle per block, then the bit-reversal swap; `non_zero_entries_count` prunes the butterflies of a
+ * zero tail (only the first min(block_len/2, nz) of every block are executed).  Same output as
+ * serial_fft -- the reference asserts it (src/fft/mod.rs:66-126, 187-279). */
+static void serial_dif_fft(const field_t *F, fe *a, const fe *omega, uint32_t log_n, uint64_t nz) {
+    const uint64_t n = (uint64_t)1 << log_n;
+    uint64_t m = 1;
+    for (uint32_t s = 0; s < log_n; s++) {
+        fe w_m; fe_pow_u64(F, &w_m, omega, m);
+        const uint64_t block_len = n / m, lim = block_len / 2 < nz ? block_len / 2 : nz;
+        for (uint64_t block = 0; block < m; block++) {
+            fe w = F->r;
+            for (uint64_t k = block * block_len; k < block * block_len + lim; k++) {
+                fe t = a[k + block_len / 2], tmp;
+                fe_sub(F, &tmp, &a[k], &t);
+                fe_mul(F, &a[k + block_len / 2], &tmp, &w);
+                fe_add(F, &a[k], &a[k], &t);
+                fe_mul(F, &w, &w, &w_m);
+            }
+        }
+        m *= 2;
+    }
+    for (uint64_t k = 0; k < n; k++) {
+        uint64_t rk = bitreverse32((uint32_t)k, log_n);
+        if (k < rk) { fe t = a[rk]; a[rk] = a[k]; a[k] = t; }
+    }
+}
+API int oracle_serial_dif_fft(int field, uint64_t *a, const uint64_t *omega, uint32_t log_n, uint64_t non_zero_entries) {
+    const field_t *F = get_field(field); if (!F || log_n > 31) return -1;
+    serial_dif_fft(F, (fe *)a, (const fe *)omega, log_n, non_zero_entries); return 0;
+}
+/* serial_lde (src/fft/lde.rs:15-126): radix-2 DIT NTT of a vector that was zero-padded by `lde_factor`;
+ * after the bit reversal index idx holds a non-zero value at stage `step` iff (idx mod lde_factor) <
+ * 2^step (is_non_zero, :27-31), and the butterflies with a structurally zero input are short-cut by
+ * the four-way match at :90-116 until the round is dense (:33-41). */
+static void serial_lde(const field_t *F, fe *a, const fe *omega, uint32_t log_n, size_t lde_factor) {
+    const uint32_t n = (uint32_t)1 << log_n;
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t rk = bitreverse32(k, log_n);
+        if (k < rk) { fe t = a[rk]; a[rk] = a[k]; a[k] = t; }
+    }
+    uint32_t m = 1, step = 0;
+    for (uint32_t s = 0; s < log_n; s++) {
+        fe w_m; fe_pow_u64(F, &w_m, omega, (uint64_t)(n / (2 * m)));
+        const int dense = (lde_factor >> step) <= 1;
+        for (uint32_t k = 0; k < n; k += 2 * m) {
+            fe w = F->r;
+            for (uint32_t j = 0; j < m; j++) {
+                const size_t odd = k + j + m, even = k + j;
+                const int odd_nz = dense || (odd & (lde_factor - 1)) < ((size_t)1 << step);
+                const int even_nz = dense || (even & (lde_factor - 1)) < ((size_t)1 << step);
+                if (odd_nz && even_nz) {
+                    fe t, tmp; fe_mul(F, &t, &a[odd], &w);
+                    fe_sub(F, &tmp, &a[even], &t); a[odd] = tmp; fe_add(F, &a[even], &a[even], &t);
+                } else if (!odd_nz && even_nz) {
+                    a[odd] = a[even];
+                } else if (odd_nz && !even_nz) {
+                    fe t, tmp; fe_mul(F, &t, &a[odd], &w); fe_neg(F, &tmp, &t); a[odd] = tmp; a[even] = t;
+                }
+                fe_mul(F, &w, &w, &w_m);
+            }
+        }
+        step++; m *= 2;
+    }
+}
+/* Polynomial::filtering_lde / coset_filtering_lde (src/polynomials/mod.rs:355-368, 484-499), serial path:
+ * (distribute_powers by the multiplicative generator,) zero-pad to n * factor, serial_lde. */
+API int oracle_filtering_lde(int field, const uint64_t *coeffs, uint32_t log_n, uint32_t factor, int coset, uint64_t *out,
+                             uint32_t cpus) {
+    const field_t *F = get_field(field); if (!F || cpus == 0 || factor == 0 || (factor & (factor - 1))) return -1;
+    uint32_t log_f = log2_floor(factor);
+    if (log_n + log_f > F->s || log_n + log_f > 31) return -2;
+    const size_t n = (size_t)1 << log_n, total = n * factor;
+    memset(out, 0, total * sizeof(fe));
+    memcpy(out, coeffs, n * sizeof(fe));
+    if (coset) distribute_powers(F, (fe *)out, n, cpus, &F->generator);
+    if (factor == 1) { fe om; domain_generator(F, log_n, &om); serial_fft(F, (fe *)out, &om, log_n); return 0; }
+    fe omega; domain_generator(F, log_n + log_f, &omega);
+    serial_lde(F, (fe *)out, &omega, log_n + log_f, factor);
+    return 0;
+}
 /* best_fft(a, worker{cpus}, omega, log_n, hint)  hint < 0 == None */
 API int oracle_best_fft(int field, uint64_t *a, const uint64_t *omega, uint32_t log_n, uint32_t cpus, long hint) {
     const field_t *F = get_field(field); if (!F || cpus == 0) return -1;

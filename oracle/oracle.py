@@ -159,6 +159,15 @@ def serial_fft_radix_4(field, a, omega, log_n):
     return a
 
 
+def serial_dif_fft(field, a, omega, log_n, non_zero_entries=None):
+    """serial_DIT_fft (src/fft/dit_fft/mod.rs:4-53); non_zero_entries prunes a zero tail."""
+    a = np.array(a, np.uint64, copy=True).reshape(-1, 4)
+    nz = a.shape[0] if non_zero_entries is None else non_zero_entries
+    _check(lib().oracle_serial_dif_fft(field, _p64(a), _p64(np.ascontiguousarray(omega, np.uint64)), log_n, C.c_uint64(nz)),
+           "serial_dif_fft")
+    return a
+
+
 def best_fft(field, a, omega, log_n, cpus=None, hint: int = -1):
     a = np.array(a, np.uint64, copy=True).reshape(-1, 4)
     cpus = cpus or default_cpus()
@@ -224,6 +233,17 @@ def lde(field, coeffs, log_n, factor, coset, cpus=None):
     # chunk-index generator (src/polynomials/mod.rs:448,575) yields the mathematically right cosets
     cpus = cpus or max(default_cpus(), factor)
     _check(lib().oracle_lde(field, _p64(coeffs), log_n, factor, int(coset), _p64(out), cpus), "lde")
+    return out
+
+
+def filtering_lde(field, coeffs, log_n, factor, coset, cpus=None):
+    """Polynomial::(coset_)filtering_lde (src/polynomials/mod.rs:355-368, 484-499) -> serial_lde
+    (src/fft/lde.rs:15-126), the zero-aware NTT of the zero-padded vector."""
+    coeffs = np.ascontiguousarray(coeffs, np.uint64).reshape(-1, 4)
+    assert coeffs.shape[0] == 1 << log_n
+    out = np.zeros((coeffs.shape[0] * factor, 4), np.uint64)
+    _check(lib().oracle_filtering_lde(field, _p64(coeffs), log_n, factor, int(coset), _p64(out), cpus or default_cpus()),
+           "filtering_lde")
     return out
 
 

@@ -157,3 +157,40 @@ def test_batch_inversion_and_evaluate_at(oracle, pymodel, fid):
     bad = a.copy()
     bad[40] = 0
     assert oracle.batch_inversion(fid, bad) is None
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_dif_variant_and_pruning(oracle, fid):
+    """test_sequential_radix4_fft / test_fft_prunning (src/fft/mod.rs:66-126, 187-279): the DIF variant
+    (src/fft/dit_fft/mod.rs) gives the radix-2 result, and pruning the butterflies of a zero tail does
+    not change it."""
+    for ln in (1, 2, 6, 10):
+        n = 1 << ln
+        a = oracle.random_elements(fid, n, seed=40 + ln)
+        om = oracle.domain_generator(fid, ln)
+        want = oracle.serial_fft(fid, a, om, ln)
+        assert np.array_equal(oracle.serial_dif_fft(fid, a, om, ln), want)
+        if ln % 2 == 0:
+            assert np.array_equal(oracle.serial_fft_radix_4(fid, a, om, ln), want)
+        nz = max(1, n // 16)
+        padded = a.copy()
+        padded[nz:] = 0
+        full = oracle.serial_fft(fid, padded, om, ln)
+        assert np.array_equal(oracle.serial_dif_fft(fid, padded, om, ln, non_zero_entries=nz), full)
+        assert np.array_equal(oracle.serial_dif_fft(fid, padded, om, ln), full)
+
+
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_filtering_lde_equals_multi_coset_lde(oracle, fid):
+    """test_lde_correctness / test_coset_lde_correctness / test_various_ldes (src/polynomials/mod.rs:988-1135):
+    the zero-aware NTT of the zero-padded vector (filtering_lde, src/fft/lde.rs) == the multi-coset LDE ==
+    the plain NTT of the zero-padded (and, for the coset form, g^j-scaled) vector."""
+    for ln, L in ((2, 16), (0, 4), (3, 1), (5, 2), (6, 8), (8, 16)):
+        a = oracle.random_elements(fid, 1 << ln, seed=70 + ln)
+        for coset in (False, True):
+            multi = oracle.lde(fid, a, ln, L, coset)
+            assert np.array_equal(oracle.filtering_lde(fid, a, ln, L, coset), multi)
+            padded = np.zeros(((1 << ln) * L, 4), np.uint64)
+            padded[: 1 << ln] = oracle.distribute_powers(fid, a, oracle.field_constants(fid)["generator"]) if coset else a
+            tl = ln + L.bit_length() - 1
+            assert np.array_equal(oracle.serial_fft(fid, padded, oracle.domain_generator(fid, tl), tl), multi)
