@@ -150,6 +150,14 @@ def test_fixed_operand_multiplier_on_host(oracle, pymodel, host_field_shim, fid)
         return out.copy()
 
     assert np.array_equal(run(7), oracle.mul(fid, a, b))
+    # the first operand may be ANY 256-bit integer (r = a*w - q*p < 2p for every a < 2^256): result is
+    # the canonical representative of a * w / R
+    rng0 = np.random.default_rng(9)
+    wide = rng0.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    wide[:2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    got = oracle.array_to_ints(run(7, wide, b))
+    Rinv = pow(F.R, -1, F.p)
+    assert got == [x * y * Rinv % F.p for x, y in zip(oracle.array_to_ints(wide), oracle.array_to_ints(b))]
     plain = [F.from_mont(x) for x in oracle.array_to_ints(b)]
     assert oracle.array_to_ints(run(8)) == [(w << 256) // F.p for w in plain]
     # truncated high product: kept = words >= 7 (+ high words of column 6); dropped part D < 14 * 2^224 and
