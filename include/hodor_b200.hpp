@@ -263,6 +263,32 @@ class Polynomial {
     }
 };
 
+// `for w in polys { w.lde(&worker, factor) }` (src/prover/mod.rs:73-76) as ONE pipelined call: the PCIe
+// copies of neighbouring polynomials overlap the transform of the current one (hodor_cuda_lde_batch).
+template <class F>
+std::vector<Polynomial<F, Values>> lde_batch(const std::vector<Polynomial<F, Coefficients>>& polys, const Worker&,
+                                             size_t factor, bool coset = false) {
+    std::vector<Polynomial<F, Values>> result;
+    if (polys.empty()) return result;
+    if (factor == 0 || (factor & (factor - 1))) throw std::logic_error("assert!(factor.is_power_of_two())");
+    const size_t n = polys[0].size();
+    uint32_t log_f = 0;
+    while (((size_t)1 << log_f) < factor) log_f++;
+    (void)Domain<F>::new_for_size(n * factor);
+    std::vector<std::vector<F>> outs(polys.size(), std::vector<F>(n * factor));
+    std::vector<const uint64_t*> in_ptrs;
+    std::vector<uint64_t*> out_ptrs;
+    for (size_t i = 0; i < polys.size(); i++) {
+        if (polys[i].size() != n) throw std::logic_error("lde_batch: polynomials must have one size");
+        in_ptrs.push_back(reinterpret_cast<const uint64_t*>(polys[i].as_ref().data()));
+        out_ptrs.push_back(reinterpret_cast<uint64_t*>(outs[i].data()));
+    }
+    check(hodor_cuda_lde_batch(in_ptrs.data(), out_ptrs.data(), (uint32_t)polys.size(), polys[0].exp, log_f, coset ? 1 : 0,
+                               F::ID));
+    for (auto& o : outs) result.push_back(Polynomial<F, Values>::adopt(std::move(o)));
+    return result;
+}
+
 // ---- IOP -------------------------------------------------------------------------------------
 template <class F>
 struct Blake2sTreeHasher {  // src/iop/blake2s_trivial_iop.rs:63-105

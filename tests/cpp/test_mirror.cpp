@@ -18,6 +18,10 @@ int oracle_batch_inversion(int field, uint64_t* a, size_t n, uint32_t cpus);
 int oracle_evaluate_at(int field, const uint64_t* coeffs, size_t n, const uint64_t* g, uint32_t cpus, uint64_t* out);
 }
 
+// compile the batch entry of the mirror for one field (exercised through the Python mirror's GPU test)
+template std::vector<Polynomial<Bn256RsFr, Values>> hodor_b200::lde_batch<Bn256RsFr>(
+    const std::vector<Polynomial<Bn256RsFr, Coefficients>>&, const Worker&, size_t, bool);
+
 static int failures = 0;
 #define CHECK(cond)                                                          \
     do {                                                                     \
