@@ -152,39 +152,75 @@ def cpu_fri_sample(log_n: int):
     return leaves / dt, cores, dt
 
 
+def bench_config(world: int) -> dict:
+    """`config` of the JSON line -- the SAME object for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "field": "bls12_381_fr", "log_n": LOG_N, "lde_factor": 1 << LOG_L, "passes": 3,
+            "l2_policy": "inputs (512 MiB) and outputs (4 GiB) exceed the 126 MB L2; no flush between steps",
+            "parallelism": f"{world} independent polynomials, one per GPU" if world > 1 else "single GPU"}
+
+
 def run_reference(args, rank: int):
+    """The reference's own CPU algorithm for the step (coset_lde_using_multiple_cosets, src/polynomials/mod.rs:
+    544-609, restated in oracle/hodor_oracle.c -- the Rust crate cannot be built in this image) on the host cores,
+    at the FULL size of the GPU arm's step: every timed step is one 2^24 -> 2^27 coset LDE.  One warm-up step is
+    full size, the others run a 2^20 sample (warming a CPU path needs no more).  HODOR_REF_BUDGET_S (default 900)
+    bounds the run: if the first full step projects past it, the arm says so and times the 2^20 sample instead."""
     if rank != 0:
         return
-    sample_log_n = 20
-    times = []
     from oracle import oracle as O
     O.build()
     cores = O.default_cpus()
-    coeffs = O.random_elements(FIELD, 1 << sample_log_n, seed=11)
-    for i in range(args.warmup + args.steps):
+    L = 1 << LOG_L
+    threads = max(cores, L)
+    budget = float(os.environ.get("HODOR_REF_BUDGET_S", "900"))
+    small = O.random_elements(FIELD, 1 << 20, seed=11)
+    t0 = time.perf_counter()
+    O.lde(FIELD, small, 20, L, True, cpus=threads)
+    small_dt = time.perf_counter() - t0
+    log_n = LOG_N
+    if small_dt * 16 * 1.3 * (args.steps + 1) > budget:
+        log_n = 20  # a host this slow cannot run `steps` full-size steps inside the budget
+    coeffs = O.random_elements(FIELD, 1 << log_n, seed=11) if log_n != 20 else small
+    for i in range(args.warmup):
+        if i == 0:
+            O.lde(FIELD, coeffs, log_n, L, True, cpus=threads)
+        else:
+            O.lde(FIELD, small, 20, L, True, cpus=threads)
+    times = []
+    for i in range(args.steps):
         t0 = time.perf_counter()
-        O.lde(FIELD, coeffs, sample_log_n, 1 << LOG_L, True, cpus=max(cores, 1 << LOG_L))
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
-    elems = (1 << sample_log_n) << LOG_L
+        out = O.lde(FIELD, coeffs, log_n, L, True, cpus=threads)
+        times.append(time.perf_counter() - t0)
+    elems = (1 << log_n) << LOG_L
     total = sum(times)
     value = elems * len(times) / total
-    fri_value, _, fri_dt = cpu_fri_sample(20)
-    sample = (f"each step = coset LDE 2^{sample_log_n} x{1 << LOG_L} (1/16 of the GPU arm's 2^{LOG_N} x{1 << LOG_L}); "
-              f"multi-coset path: one serial_fft thread per coset, distribute_powers on all {cores} cores")
+    # the committed form of the step (what `e2e` of the GPU arm does on top of the LDE): Blake2sIopTree::create
+    t0 = time.perf_counter()
+    O.merkle_create(FIELD, out, cpus=cores)
+    tree_dt = time.perf_counter() - t0
+    del out
+    fri_value, _, fri_dt = cpu_fri_sample(FRI_LOG_N if log_n == LOG_N else 20)
+    full = log_n == LOG_N
+    sample = (f"every timed step = the full coset LDE 2^{log_n} x{L} ({'the GPU arm\'s workload' if full else 'a 1/16 SAMPLE: host too slow for the budget'}); "
+              f"multi-coset path as the reference runs it on {cores} cores: one serial_fft thread per coset "
+              f"(its num_cpus_hint rule, src/polynomials/mod.rs:549-558), distribute_powers and the interleave on all cores; "
+              f"2^20 sample for comparison: {small_dt:.2f} s")
+    cfg = bench_config(args.gpus)
+    if not full:
+        cfg["reference_sample_log_n"] = log_n
     line = {
         "impl": "reference", "metric": "ntt_field_elems_per_sec", "value": value, "unit": "field-elems/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery)",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "field": "bls12_381_fr", "log_n": LOG_N, "lde_factor": 1 << LOG_L,
-                   "sample": f"each timed step is the same transform at 2^{sample_log_n} (1/16 of the workload) on the host cores",
-                   "reference_impl": "C restatement of hodor's crossbeam path (Rust toolchain unavailable)"},
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "field-elems/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "field-elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_impl": "C restatement of hodor's crossbeam path (Rust toolchain unavailable): oracle/hodor_oracle.c",
+        "lde_commit": {"workload": "the same LDE followed by Blake2sIopTree::create on its 2^27 values (prover/mod.rs:73-80)",
+                       "tree_s": tree_dt, "lde_s": total / len(times),
+                       "value": elems / (total / len(times) + tree_dt), "unit": "field-elems/s"},
         "fri": {"metric": "fri_merkle_leaves_per_sec", "value": fri_value, "unit": "leaves/s",
-                "sample": f"FRI commit chain on 2^20 values, blowup {FRI_L}, {cores} cores, {fri_dt:.2f} s"},
+                "sample": f"FRI commit chain on 2^{FRI_LOG_N if full else 20} values, blowup {FRI_L}, {cores} cores, {fri_dt:.2f} s"},
         "gpu_launches": 0,
     }
     emit(line)
@@ -377,58 +413,133 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                   "api": "hodor_cuda_fri_commit (host LDE values, pinned) + hodor_cuda_fri_summary"}
     del d_vals, h_vals
 
-    # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + LDE + D2H every step.
-    # A prover lifts all its registers in a row (src/prover/mod.rs:73-76), so the call measured is the
-    # batch entry point: e2e_steps polynomials, each copied in, transformed and copied out inside the
-    # timed region, with the copies of neighbouring polynomials overlapping the transform.  The
-    # one-polynomial-per-call figure (nothing to overlap with) is reported next to it.
+    # ---- end to end through the host-pointer C ABI, host buffers in, copies inside the timed region.
+    # The call a prover makes per register is "lift and commit" (src/prover/mod.rs:73-80: `w.lde(..)` then
+    # `I::create(&lde)`): hodor_cuda_lde_commit_batch takes the coefficients from (pinned) host memory, keeps the
+    # LDE and its Merkle tree in HBM behind a handle and returns the 32-byte root -- MORE work per step than
+    # `value` (the tree over the 2^27 values is built as well), with only the root crossing PCIe on the way
+    # back.  The raw-LDE entry points (4 GiB D2H per step) are reported next to it as `raw_lde`.
     all_cpus = os.sched_getaffinity(0)
     near = gpu_local_cpus(local_rank)
     if near:
         os.sched_setaffinity(0, near[0])  # allocate (first-touch) the pinned buffers on the GPU's NUMA node
     h_in = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
+    h_in.numpy().view(np.uint64)[:] = coeffs
+    e2e_steps = max(2, args.steps)
+    CH = 4  # handles alive at once: 4 x (4 GiB values + 4 GiB nodes)
+    want_root = None
+
+    def commit_chunk(src_ptr, count):
+        ins = (C.c_void_p * count)(*[src_ptr] * count)
+        outs = (C.c_void_p * count)()
+        roots = np.zeros((count, 32), np.uint8)
+        _ffi.check(lib.hodor_cuda_lde_commit_batch(ins, count, LOG_N, LOG_L, 1, 0, outs, roots.ctypes.data_as(_ffi.u8p), FIELD))
+        for i in range(count):
+            lib.hodor_cuda_tree_free(outs[i])
+        return roots
+
+    def e2e_commit(src_ptr, steps):
+        done, r = 0, None
+        while done < steps:
+            m = min(CH, steps - done)
+            r = commit_chunk(src_ptr, m)
+            done += m
+        return r
+
+    want_root = e2e_commit(h_in.data_ptr(), CH)[0].tobytes()  # warm-up: pool blocks, tables
+    barrier()
+    l0 = dev.launch_count()
+    t0 = time.perf_counter()
+    got_roots = e2e_commit(h_in.data_ptr(), e2e_steps)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e_launches = dev.launch_count() - l0
+    # device-only time of the same lift-and-commit (coefficients already in HBM)
+    d_ins = (C.c_void_p * 1)(d_coeffs.data_ptr())
+    d_outs = (C.c_void_p * 1)()
+
+    def commit_dev():
+        _ffi.check(lib.hodor_cuda_lde_commit_batch(d_ins, 1, LOG_N, LOG_L, 1, 1, d_outs, None, FIELD))
+        lib.hodor_cuda_tree_free(d_outs[0])
+
+    torch.cuda.synchronize()
+    commit_dev()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        commit_dev()
+    commit_dev_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+    cprof = profile(commit_dev)
+    # the same call from PAGEABLE host memory (what a Rust Vec<F> is): the copy is staged by the driver
+    pageable = np.array(coeffs, copy=True)
+    commit_chunk(pageable.ctypes.data, 1)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        commit_chunk(pageable.ctypes.data, 2)
+    pageable_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 4
+    # root of the committed LDE == root of a tree built over the device-timed LDE output
+    d_nodes = dev.empty_elems(n * L)
+    d_root = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    lde_step()
+    dev.merkle_build(d_out, n * L, d_nodes, FIELD, root=d_root)
+    same_root = bytes(d_root.cpu().numpy().tobytes()) == want_root == got_roots[-1].tobytes()
+    del d_nodes
+
+    # raw LDE through the host-pointer ABI (the reference's own signature: values back in host memory)
     h_outs = [torch.empty((n * L, 4), dtype=torch.int64, pin_memory=True) for _ in range(2)]
     for h in h_outs:
         h.zero_()
-    h_in.numpy().view(np.uint64)[:] = coeffs
-    e2e_steps = max(2, args.steps)
+    raw_steps = min(e2e_steps, 4)
 
     def e2e_single():
         _ffi.check(lib.hodor_cuda_lde(C.cast(h_in.data_ptr(), _ffi.u64p), LOG_N, LOG_L, 1,
                                       C.cast(h_outs[0].data_ptr(), _ffi.u64p), FIELD))
 
-    ins_arr = (_ffi.u64p * e2e_steps)(*[C.cast(h_in.data_ptr(), _ffi.u64p)] * e2e_steps)
-    outs_arr = (_ffi.u64p * e2e_steps)(*[C.cast(h_outs[i % 2].data_ptr(), _ffi.u64p) for i in range(e2e_steps)])
+    ins_arr = (_ffi.u64p * raw_steps)(*[C.cast(h_in.data_ptr(), _ffi.u64p)] * raw_steps)
+    outs_arr = (_ffi.u64p * raw_steps)(*[C.cast(h_outs[i % 2].data_ptr(), _ffi.u64p) for i in range(raw_steps)])
 
     def e2e_batch():
-        _ffi.check(lib.hodor_cuda_lde_batch(ins_arr, outs_arr, e2e_steps, LOG_N, LOG_L, 1, FIELD))
+        _ffi.check(lib.hodor_cuda_lde_batch(ins_arr, outs_arr, raw_steps, LOG_N, LOG_L, 1, FIELD))
 
     e2e_single()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(2):
-        e2e_single()
+    e2e_single()
     torch.cuda.synchronize()
-    single_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 2
+    single_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_batch()  # warm-up: staging buffers come from the pool afterwards
     barrier()
     t0 = time.perf_counter()
     e2e_batch()
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    raw_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / raw_steps
     same = all(bool(np.array_equal(h.numpy()[: 1 << 16], d_out[: 1 << 16].cpu().numpy())) and
                bool(np.array_equal(h.numpy()[-(1 << 16):], d_out[-(1 << 16):].cpu().numpy())) for h in h_outs)
+    del h_outs
+    pg_out = np.zeros((n * L, 4), np.uint64)
+    t0 = time.perf_counter()
+    _ffi.check(lib.hodor_cuda_lde(_p(pageable), LOG_N, LOG_L, 1, _p(pg_out), FIELD))
+    raw_pageable_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    del pg_out, pageable
     e2e = {"value": world * n * L / (e2e_ms * 1e-3), "unit": "field-elems/s", "h2d_bytes_per_step": 32 * n,
-           "d2h_bytes_per_step": 32 * n * L, "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "api": "hodor_cuda_lde_batch (host pointers, pinned; one call lifts `steps` polynomials, copies pipelined "
-                  "against the transforms)",
-           "single_call": {"api": "hodor_cuda_lde (one polynomial per call)", "ms_per_step": single_ms,
-                           "value": world * n * L / (single_ms * 1e-3)},
-           "timer": "host perf_counter around the synchronous C-ABI call, max over ranks",
+           "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "hodor_cuda_lde_commit_batch (host coefficients, pinned; per polynomial: H2D, coset LDE 2^24 -> 2^27, "
+                  "Blake2s Merkle tree over the 2^27 values, root D2H; LDE and tree stay in HBM behind a handle; "
+                  f"{CH} polynomials per call, H2D of the next one overlaps the kernels) + hodor_cuda_tree_free",
+           "work_per_step": "the LDE of `value` PLUS the commitment to it (2^28 - 1 Blake2s compressions)",
+           "device_only_ms_per_step": commit_dev_ms,
+           "kernels": {k: {"launches": r["count"], "total_ms": r["total_ms"]} for k, r in cprof.items()},
+           "gpu_launches": e2e_launches,
+           "pageable_host_memory": {"ms_per_step": pageable_ms, "value": world * n * L / (pageable_ms * 1e-3),
+                                    "note": "same call from an unpinned numpy buffer (what a Rust Vec<F> is)"},
+           "timer": "host perf_counter around the synchronous C-ABI calls, max over ranks",
            "host_buffers": (f"pinned, allocated on NUMA node {near[1]} next to the GPU ({len(near[0])} CPUs)"
                             if near and near[1] not in ("-1", "") else "pinned; the box exposes no NUMA topology"),
-           "matches_device_result": same}
-    del h_in, h_outs
+           "root_matches_device_result": bool(same_root),
+           "raw_lde": {"api": "hodor_cuda_lde_batch (values copied back: 4 GiB D2H per polynomial)", "ms_per_step": raw_ms,
+                       "value": world * n * L / (raw_ms * 1e-3), "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n * L,
+                       "single_call_ms": single_ms, "single_call_pageable_ms": raw_pageable_ms,
+                       "matches_device_result": same}}
+    del h_in
     os.sched_setaffinity(0, all_cpus)
 
     # ---- the sharded four-step NTT (only path with a collective), N > 1
@@ -473,16 +584,39 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "timer": "host perf_counter, barrier + synchronize both sides, max over ranks"}
         del d_shared
 
+    # ---- configs[4], single-GPU column: forward NTT 2^18 .. 2^28 (the sharded columns are `sharded_ntt`)
     sweep = None
-    if args.sweep and world == 1:
+    if world == 1 and not args.no_sweep:
         sweep = []
-        for ln in range(18, 29, 2):
+        for ln in range(18, 29):
             a = dev.to_device(synthetic_elements(1 << ln, seed=ln))
             b = dev.empty_elems(1 << ln)
-            ms = timed(lambda: dev.fft(a, b, ln, False, FIELD), 5, 3) / 5
+            reps = 5 if ln <= 26 else 3
+            ms = timed(lambda: dev.fft(a, b, ln, False, FIELD), reps, 3) / reps
             sweep.append({"log_n": ln, "ms": ms, "value": (1 << ln) / (ms * 1e-3),
                           "hbm_frac": 64 * (1 << ln) / (ms * 1e-3) / 1e9 / peak_gbs})
             del a, b
+        if rank == 0 and not args.no_cpu:
+            # the reference's best_fft (parallel_fft over all host cores, src/fft/fft.rs:68-125) per size:
+            # measured up to 2^24, extrapolated with n log n beyond (labelled)
+            from oracle import oracle as O
+            O.build()
+            cpu_ms = {}
+            for ln in (18, 20, 22, 24):
+                x = O.random_elements(FIELD, 1 << ln, seed=ln)
+                t0 = time.perf_counter()
+                O.best_fft(FIELD, x, O.domain_generator(FIELD, ln), ln)
+                cpu_ms[ln] = (time.perf_counter() - t0) * 1e3
+            for row in sweep:
+                ln = row["log_n"]
+                if ln in cpu_ms:
+                    row["cpu_ms"], row["cpu_kind"] = cpu_ms[ln], "measured"
+                else:
+                    base = max(k for k in cpu_ms if k <= ln) if ln > 18 else 18
+                    row["cpu_ms"] = cpu_ms[base] * ((1 << ln) * ln) / ((1 << base) * base)
+                    row["cpu_kind"] = f"extrapolated from 2^{base} by n log n"
+                row["speedup_vs_cpu"] = row["cpu_ms"] / row["ms"]
+                row["cpu_cores"] = O.default_cpus()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -499,10 +633,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8 x u32 Montgomery limbs, INT32 pipe)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "field": "bls12_381_fr", "log_n": LOG_N, "lde_factor": L, "passes": 3,
-                       "l2_policy": "inputs (512 MiB) and outputs (4 GiB) exceed the 126 MB L2; no flush between steps",
-                       "parallelism": f"{world} independent polynomials, one per GPU" if world > 1 else "single GPU"},
+            "config": bench_config(world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "ntt": ntt, "fri": fri,
         }
@@ -521,7 +652,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--sweep", action="store_true", help="add the 2^18..2^28 NTT size sweep (configs[4])")
+    ap.add_argument("--sweep", action="store_true", help="sharded legs: every even size 2^18..2^28 instead of 2^24/2^26/2^28")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the single-GPU NTT size sweep 2^18..2^28 (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -10,7 +10,7 @@ from ._ffi import (BLS12_381_FR, BN254_FR, STARK252, FIELD_NAMES, HodorError, Sy
 from .field import BN256_RS_FR  # noqa: F401
 from .domains import Domain  # noqa: F401
 from .polynomials import COEFFICIENTS, VALUES, Polynomial, Worker, lde_batch  # noqa: F401
-from .iop import (Blake2sIopTree, Blake2sLeafEncoder, Blake2sTreeHasher, DeviceIOP, TrivialBlake2sIOP,  # noqa: F401
+from .iop import (Blake2sIopTree, Blake2sLeafEncoder, Blake2sTreeHasher, CommittedOracle, DeviceIOP, TrivialBlake2sIOP,  # noqa: F401
                   TrivialBlake2sIopQuery, TrivialCombiner)
 from .fri import FRIProof, FRIProofPrototype, NaiveFriIop  # noqa: F401
 

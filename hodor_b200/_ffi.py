@@ -54,6 +54,7 @@ _SIGS = {
     "hodor_cuda_init": (C.c_int, [C.c_int]),
     "hodor_cuda_shutdown": (None, []),
     "hodor_cuda_last_error": (C.c_char_p, []),
+    "hodor_cuda_last_error_code": (C.c_int, []),
     "hodor_cuda_workspace_bytes": (C.c_size_t, []),
     "hodor_cuda_launch_count": (C.c_uint64, []),
     "hodor_cuda_selftest_mul_pre": (C.c_int, [C.c_int]),
@@ -89,6 +90,18 @@ _SIGS = {
     "hodor_cuda_batch_inversion": (C.c_int, [u64p, C.c_uint64, C.c_int]),
     "hodor_cuda_evaluate_at": (C.c_int, [u64p, C.c_uint64, u64p, u64p, C.c_int]),
     "hodor_cuda_merkle_build": (C.c_int, [u64p, C.c_uint64, u8p, C.c_int]),
+    "hodor_cuda_lde_commit": (vp, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, u8p, C.c_int]),
+    "hodor_cuda_lde_commit_batch": (C.c_int, [C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                              C.POINTER(vp), u8p, C.c_int]),
+    "hodor_cuda_tree_commit": (vp, [vp, C.c_uint64, C.c_int, u8p, C.c_int]),
+    "hodor_cuda_tree_free": (None, [vp]),
+    "hodor_cuda_tree_size": (C.c_uint64, [vp]),
+    "hodor_cuda_tree_values": (vp, [vp]),
+    "hodor_cuda_tree_nodes": (vp, [vp]),
+    "hodor_cuda_tree_root": (C.c_int, [vp, u8p, u64p]),
+    "hodor_cuda_tree_query": (C.c_int, [vp, C.c_uint64, u64p, u8p]),
+    "hodor_cuda_tree_query_batch": (C.c_int, [vp, u64p, C.c_uint32, u64p, u8p]),
+    "hodor_cuda_tree_read": (C.c_int, [vp, C.c_uint64, C.c_uint64, u64p, u8p]),
     "hodor_cuda_fri_commit": (vp, [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "hodor_cuda_fri_free": (None, [vp]),
     "hodor_cuda_fri_num_steps": (C.c_int, [vp]),
@@ -128,6 +141,12 @@ for _name, (_res, _args) in _SIGS.items():
 def last_error() -> str:
     msg = lib.hodor_cuda_last_error()
     return msg.decode() if msg else ""
+
+
+def raise_last() -> None:
+    """For entry points that return a handle or NULL: raise with the code the library recorded."""
+    code = int(lib.hodor_cuda_last_error_code()) or ERR_CUDA
+    check(code if code < 0 else ERR_CUDA)
 
 
 def check(rc: int) -> int:

@@ -26,8 +26,21 @@ int cuda_fail(cudaError_t e, const char* what) {
     return g_last_code;
 }
 
+// The current device is a per-host-thread property: a thread other than the one that called
+// hodor_cuda_init would otherwise allocate and launch on device 0.
+static thread_local int tl_device = -1;
 Ctx* ctx() {
-    if (g_ctx == nullptr) fail(HODOR_ERR_CUDA, "hodor_cuda_init() has not been called (or failed): no GPU context, and there is no CPU path");
+    if (g_ctx == nullptr) {
+        fail(HODOR_ERR_CUDA, "hodor_cuda_init() has not been called (or failed): no GPU context, and there is no CPU path");
+        return nullptr;
+    }
+    if (tl_device != g_ctx->device) {
+        if (cudaSetDevice(g_ctx->device) != cudaSuccess) {
+            cuda_fail(cudaGetLastError(), "cudaSetDevice");
+            return nullptr;
+        }
+        tl_device = g_ctx->device;
+    }
     return g_ctx;
 }
 
@@ -41,6 +54,20 @@ int Ctx::ensure_workspace(size_t bytes) {
     }
     HODOR_CUDA_TRY(cudaMalloc(&ws, bytes));
     ws_bytes = bytes;
+    return HODOR_OK;
+}
+
+int Ctx::ws_acquire(size_t bytes, cudaStream_t st) {
+    int rc = ensure_workspace(bytes);  // growing synchronises the whole device first
+    if (rc) return rc;
+    if (ws_used && ws_stream != st) HODOR_CUDA_TRY(cudaStreamWaitEvent(st, ws_event, 0));
+    return HODOR_OK;
+}
+int Ctx::ws_release(cudaStream_t st) {
+    if (!ws_event) HODOR_CUDA_TRY(cudaEventCreateWithFlags(&ws_event, cudaEventDisableTiming));
+    HODOR_CUDA_TRY(cudaEventRecord(ws_event, st));
+    ws_stream = st;
+    ws_used = true;
     return HODOR_OK;
 }
 
@@ -94,7 +121,7 @@ void Ctx::pool_free(void* p) {
     pool_live.erase(it);
     size_t cached = 0;
     for (auto& b : pool_free_list) cached += b.second;
-    if (pool_free_list.size() >= 8 || cached + bytes > ((size_t)16 << 30)) cudaFree(p);
+    if (pool_free_list.size() >= 8 || cached + bytes > pool_cache_cap) cudaFree(p);
     else pool_free_list.emplace_back(p, bytes);
 }
 
@@ -229,6 +256,7 @@ int hodor_cuda_init(int device) {
     }
     if (device < 0 || device >= n) return fail(HODOR_ERR_INVALID_ARG, "device index out of range");
     HODOR_CUDA_TRY(cudaSetDevice(device));
+    tl_device = device;
     cudaDeviceProp prop;
     HODOR_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -244,6 +272,7 @@ int hodor_cuda_init(int device) {
     HODOR_CUDA_TRY(cudaMalloc((void**)&c->small, 4096));
     c->key = b2s_keyed_state();
     if (const char* mb = getenv("HODOR_TABLE_BUDGET_MB")) c->full_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
+    if (const char* mb = getenv("HODOR_POOL_CACHE_MB")) c->pool_cache_cap = (size_t)strtoull(mb, nullptr, 10) << 20;
     g_ctx = c.release();
     return HODOR_OK;
 }
@@ -269,6 +298,7 @@ void hodor_cuda_shutdown(void) {
         cudaEventDestroy(r.stop);
     }
     for (auto e : g_ctx->event_pool) cudaEventDestroy(e);
+    if (g_ctx->ws_event) cudaEventDestroy(g_ctx->ws_event);
     cudaFree(g_ctx->small);
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_in);
@@ -278,6 +308,7 @@ void hodor_cuda_shutdown(void) {
 }
 
 const char* hodor_cuda_last_error(void) { return g_last_error.c_str(); }
+int hodor_cuda_last_error_code(void) { return g_last_code; }
 
 size_t hodor_cuda_workspace_bytes(void) {
     Ctx* c = g_ctx;
@@ -792,6 +823,213 @@ int hodor_cuda_merkle_build(const uint64_t* leaves, uint64_t n, uint8_t* nodes, 
     HODOR_CUDA_TRY(cudaMemcpyAsync(nodes, c->io[1], n * 32, cudaMemcpyDeviceToHost, c->stream));
     HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return HODOR_OK;
+}
+
+// ---- committed oracles: values + Merkle tree resident in HBM behind a handle ------------------------
+// What Prover::prove does with every register: `w.lde(..)` then `I::create(&lde)` (src/prover/mod.rs:73-80,
+// :91-95), keeping both for the query phase (:142-151, IOP::query src/iop/blake2s_trivial_iop.rs:324-338).
+// Only the root (32 B) crosses PCIe at commit time and log2(n) digests + one value per query.
+struct hodor_tree {
+    int field_id = 0;
+    uint64_t n = 0;
+    uint4* block = nullptr;         // one allocation: [values] | nodes | root | challenge | path scratch
+    const uint4* values = nullptr;  // inside `block`, or borrowed from the caller
+    uint4* nodes = nullptr;
+    uint4* root = nullptr;
+    uint4* chal = nullptr;
+    uint4* path = nullptr;          // 64 digests + 1 element per query, TREE_QUERY_SLOTS queries
+};
+static constexpr uint32_t TREE_QUERY_SLOTS = 64;
+
+static void tree_destroy(hodor_tree* t) {
+    if (!t) return;
+    Ctx* c = g_ctx;
+    if (t->block) c ? c->pool_free(t->block) : (void)cudaFree(t->block);
+    delete t;
+}
+
+// allocates the handle; own_values: room for n values in front of the nodes
+static hodor_tree* tree_alloc(Ctx* c, int field_id, uint64_t n, bool own_values) {
+    std::unique_ptr<hodor_tree, void (*)(hodor_tree*)> t(new hodor_tree(), tree_destroy);
+    t->field_id = field_id;
+    t->n = n;
+    const size_t slots = (own_values ? n : 0) + n + 2 + (size_t)TREE_QUERY_SLOTS * 66;
+    t->block = (uint4*)c->pool_alloc(slots * 32);
+    if (!t->block) return nullptr;
+    uint4* cur = t->block;
+    if (own_values) {
+        t->values = cur;
+        cur += 2 * n;
+    }
+    t->nodes = cur;
+    cur += 2 * n;
+    t->root = cur;
+    t->chal = cur + 2;
+    t->path = cur + 4;
+    return t.release();
+}
+
+hodor_tree* hodor_cuda_tree_commit(const uint64_t* values, uint64_t n, int values_on_device, uint8_t root[32], int field_id) {
+    Ctx* c = ctx();
+    if (!c) return nullptr;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const FieldOps* ops = field_ops(field_id);
+    if (!ops) return nullptr;
+    if (!is_pow2(n) || n < 2 || values == nullptr) {  // reference: assert!(num_leafs == num_leafs.next_power_of_two())
+        fail(HODOR_ERR_INVALID_ARG, "tree_commit: leaf count must be a power of two >= 2");
+        return nullptr;
+    }
+    std::unique_ptr<hodor_tree, void (*)(hodor_tree*)> t(tree_alloc(c, field_id, n, !values_on_device), tree_destroy);
+    if (!t) return nullptr;
+    cudaStream_t st = c->stream;
+    if (values_on_device) {
+        t->values = (const uint4*)values;
+    } else if (cudaMemcpyAsync((void*)t->values, values, n * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(values)");
+        return nullptr;
+    }
+    int rc = do_merkle(*c, ops, t->values, n, t->nodes, t->root, t->chal, st);
+    if (!rc && root && cudaMemcpyAsync(root, t->root, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(root)");
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "tree_commit sync");
+    if (rc) return nullptr;
+    return t.release();
+}
+
+// `count` polynomials of one shape: H2D of polynomial i+1 (second stream, double-buffered staging)
+// overlaps the LDE + tree build of polynomial i.  trees[i] / roots + 32*i receive the results.
+int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, uint32_t log_n, uint32_t log_factor, int coset,
+                                int coeffs_on_device, hodor_tree** trees, uint8_t* roots, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 32 || log_n + log_factor > 34 || log_n + log_factor < 1)
+        return fail(HODOR_ERR_INVALID_ARG, "lde_commit: need 2 <= n * factor <= 2^34");
+    if (count == 0) return HODOR_OK;
+    if (coeffs == nullptr || trees == nullptr) return fail(HODOR_ERR_INVALID_ARG, "lde_commit: NULL pointer table");
+    for (uint32_t i = 0; i < count; i++) {
+        if (coeffs[i] == nullptr) return fail(HODOR_ERR_INVALID_ARG, "lde_commit: NULL buffer");
+        trees[i] = nullptr;
+    }
+    {
+        Fe probe;
+        int rc = ops->h_domain_generator(log_n + log_factor, probe);
+        if (rc) return fail(rc, "LDE domain larger than the field's 2-adicity");
+    }
+    const size_t n = (size_t)1 << log_n, total = n << log_factor;
+    const uint32_t nbuf = coeffs_on_device ? 0 : (count < 2 ? 1 : 2);
+    void* in_buf[2] = {nullptr, nullptr};
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr};
+    int rc = HODOR_OK;
+    for (uint32_t b = 0; b < nbuf && rc == HODOR_OK; b++) {
+        in_buf[b] = c->pool_alloc(n * 32);
+        if (!in_buf[b]) rc = HODOR_ERR_OOM;
+        cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming);
+    }
+    auto step = [&](uint32_t i) -> int {
+        hodor_tree* t = tree_alloc(c, field_id, total, true);
+        if (!t) return HODOR_ERR_OOM;
+        trees[i] = t;
+        const uint4* src = (const uint4*)coeffs[i];
+        if (!coeffs_on_device) {
+            const uint32_t b = i % nbuf;
+            if (i >= nbuf) HODOR_CUDA_TRY(cudaStreamWaitEvent(c->copy_in, comp_done[b], 0));  // in_buf[b] consumed
+            HODOR_CUDA_TRY(cudaMemcpyAsync(in_buf[b], coeffs[i], n * 32, cudaMemcpyHostToDevice, c->copy_in));
+            HODOR_CUDA_TRY(cudaEventRecord(in_done[b], c->copy_in));
+            HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, in_done[b], 0));
+            src = (const uint4*)in_buf[b];
+        }
+        int r = do_lde(*c, ops, src, (uint4*)t->values, log_n, log_factor, coset, c->stream);
+        if (r) return r;
+        if (!coeffs_on_device) HODOR_CUDA_TRY(cudaEventRecord(comp_done[i % nbuf], c->stream));
+        r = do_merkle(*c, ops, t->values, total, t->nodes, t->root, t->chal, c->stream);
+        if (r) return r;
+        if (roots) HODOR_CUDA_TRY(cudaMemcpyAsync(roots + 32 * (size_t)i, t->root, 32, cudaMemcpyDeviceToHost, c->stream));
+        return HODOR_OK;
+    };
+    for (uint32_t i = 0; i < count && rc == HODOR_OK; i++) rc = step(i);
+    cudaStreamSynchronize(c->copy_in);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    for (uint32_t b = 0; b < nbuf; b++) {
+        if (in_done[b]) cudaEventDestroy(in_done[b]);
+        if (comp_done[b]) cudaEventDestroy(comp_done[b]);
+        if (in_buf[b]) c->pool_free(in_buf[b]);
+    }
+    if (rc == HODOR_OK && e != cudaSuccess) rc = cuda_fail(e, "lde_commit");
+    if (rc) {
+        for (uint32_t i = 0; i < count; i++) {
+            tree_destroy(trees[i]);
+            trees[i] = nullptr;
+        }
+    }
+    return rc;
+}
+
+hodor_tree* hodor_cuda_lde_commit(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, int coset, int coeffs_on_device,
+                                  uint8_t root[32], int field_id) {
+    hodor_tree* t = nullptr;
+    const uint64_t* tab[1] = {coeffs};
+    if (hodor_cuda_lde_commit_batch(tab, 1, log_n, log_factor, coset, coeffs_on_device, &t, root, field_id)) return nullptr;
+    return t;
+}
+
+void hodor_cuda_tree_free(hodor_tree* t) {
+    Ctx* c = g_ctx;
+    if (c) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        cudaStreamSynchronize(c->stream);
+        tree_destroy(t);
+    } else {
+        tree_destroy(t);
+    }
+}
+uint64_t hodor_cuda_tree_size(const hodor_tree* t) { return t ? t->n : 0; }
+const void* hodor_cuda_tree_values(const hodor_tree* t) { return t ? (const void*)t->values : nullptr; }
+const void* hodor_cuda_tree_nodes(const hodor_tree* t) { return t ? (const void*)t->nodes : nullptr; }
+int hodor_cuda_tree_root(const hodor_tree* t, uint8_t root[32], uint64_t challenge[4]) {
+    LOCKED_CTX();
+    if (!t) return fail(HODOR_ERR_INVALID_ARG, "null tree handle");
+    if (root) HODOR_CUDA_TRY(cudaMemcpyAsync(root, t->root, 32, cudaMemcpyDeviceToHost, c->stream));
+    if (challenge) HODOR_CUDA_TRY(cudaMemcpyAsync(challenge, t->chal, 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+int hodor_cuda_tree_read(const hodor_tree* t, uint64_t first, uint64_t count, uint64_t* values, uint8_t* nodes) {
+    LOCKED_CTX();
+    if (!t) return fail(HODOR_ERR_INVALID_ARG, "null tree handle");
+    if (first > t->n || count > t->n - first) return fail(HODOR_ERR_INVALID_ARG, "tree_read: range out of bounds");
+    if (values) HODOR_CUDA_TRY(cudaMemcpyAsync(values, t->values + 2 * first, count * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (nodes) HODOR_CUDA_TRY(cudaMemcpyAsync(nodes, t->nodes + 2 * first, count * 32, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+// `count` queries in one launch and one pair of copies: values[i] (4 u64) and paths + i * 32 * log2(n)
+int hodor_cuda_tree_query_batch(const hodor_tree* t, const uint64_t* natural_indices, uint32_t count, uint64_t* values,
+                                uint8_t* paths) {
+    LOCKED_CTX();
+    if (!t) return fail(HODOR_ERR_INVALID_ARG, "null tree handle");
+    if (count && natural_indices == nullptr) return fail(HODOR_ERR_INVALID_ARG, "tree_query: NULL index table");
+    for (uint32_t i = 0; i < count; i++)
+        if (natural_indices[i] >= t->n) return fail(HODOR_ERR_INVALID_ARG, "query index out of range");  // reference: assert!
+    const int len = (int)log2u(t->n);
+    cudaStream_t st = c->stream;
+    for (uint32_t done = 0; done < count; done += TREE_QUERY_SLOTS) {
+        const uint32_t m = count - done < TREE_QUERY_SLOTS ? count - done : TREE_QUERY_SLOTS;
+        uint64_t* d_idx = (uint64_t*)(c->small + 96);  // 64 indices = 512 B of the 4 KiB scalar scratch
+        HODOR_CUDA_TRY(cudaMemcpyAsync(d_idx, natural_indices + done, m * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        int rc = merkle_paths_gather(*c, t->nodes, t->values, t->n, d_idx, m, t->path, st);
+        if (rc) return rc;
+        for (uint32_t i = 0; i < m; i++) {
+            const uint4* slot = t->path + 2 * 66 * (size_t)i;
+            if (paths) HODOR_CUDA_TRY(cudaMemcpyAsync(paths + (size_t)(done + i) * 32 * len, slot, (size_t)len * 32, cudaMemcpyDeviceToHost, st));
+            if (values) HODOR_CUDA_TRY(cudaMemcpyAsync(values + 4 * (size_t)(done + i), slot + 2 * 64, 32, cudaMemcpyDeviceToHost, st));
+        }
+        HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return len;
+}
+int hodor_cuda_tree_query(const hodor_tree* t, uint64_t natural_index, uint64_t value[4], uint8_t* path) {
+    return hodor_cuda_tree_query_batch(t, &natural_index, 1, value, path);
 }
 
 // ---- per-kernel timing (bench.py's live roofline) ------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,8 @@ struct Ctx {
     size_t full_bytes = 0;
     size_t full_budget = (size_t)24 << 30;  // HODOR_TABLE_BUDGET_MB overrides; 0 disables
 
+    // freed prototype / tree / staging blocks kept for reuse (a committed 2^27 oracle is 8 GiB); HODOR_POOL_CACHE_MB
+    size_t pool_cache_cap = (size_t)40 << 30;
     std::vector<std::pair<void*, size_t>> pool_free_list;
     std::map<void*, size_t> pool_live;
     void* pool_alloc(size_t bytes);
@@ -92,6 +95,20 @@ struct Ctx {
 
     int ensure_workspace(size_t bytes);
     int ensure_io(int which, size_t bytes);
+
+    // The workspace is shared by every multi-kernel entry point (multi-pass NTT / LDE, batch_inversion,
+    // evaluate_at) and `_dev` calls may arrive on different caller streams: the host-side mutex orders the
+    // enqueues, not the execution.  ws_acquire makes `st` wait for the last user of the workspace when that
+    // was another stream; ws_release records the new last use.  Same-stream callers pay nothing.
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
+    int ws_acquire(size_t bytes, cudaStream_t st);
+    int ws_release(cudaStream_t st);
+
+    // kernels whose dynamic shared memory attribute has been raised on this context's device
+    std::set<const void*> configured_kernels;
+    std::map<uint64_t, Fe> inv_cache;  // (field, log_n) -> omega_N^-1 of the FRI domain
     cudaEvent_t take_event();
 };
 
@@ -183,5 +200,7 @@ const FieldOps* field_ops(int field_id);
 int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st);
 int merkle_path_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
                        cudaStream_t st);
+int merkle_paths_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, const uint64_t* d_indices,
+                        uint32_t count, uint4* out, cudaStream_t st);
 
 }  // namespace hodor

@@ -313,12 +313,11 @@ struct Ops {
     static int launch_pass(Ctx& c, const NttPass& p, dim3 grid, cudaStream_t st) {
         auto kern = ntt_pass_kernel<F, B, SCALE_IN, LAST>;
         constexpr size_t smem = (size_t)256 << B;
-        static bool configured = false;  // guarded by Ctx::mu
-        if (!configured) {
+        if (!c.configured_kernels.count((const void*)kern)) {  // per context: survives neither shutdown nor a re-init elsewhere
             HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                 cudaSharedmemCarveoutMaxShared));
-            configured = true;
+            c.configured_kernels.insert((const void*)kern);
         }
         {
             ProfScope ps(c, st, LAST ? "ntt_pass_last" : (SCALE_IN ? "ntt_pass_first_scaled" : "ntt_pass"));
@@ -432,10 +431,9 @@ struct Ops {
             p.tw = flat->lo;
             auto kern = ntt_small_kernel<F>;
             const size_t smem = n * sizeof(Fe);
-            static bool configured = false;
-            if (!configured) {
+            if (!c.configured_kernels.count((const void*)kern)) {
                 HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32));
-                configured = true;
+                c.configured_kernels.insert((const void*)kern);
             }
             unsigned threads = (unsigned)(n / 2 < 32 ? 32 : (n / 2 > 1024 ? 1024 : n / 2));
             {
@@ -447,7 +445,7 @@ struct Ops {
         }
 
         // ---- multi-pass ----
-        rc = c.ensure_workspace(n * L * sizeof(Fe));
+        rc = c.ws_acquire(n * L * sizeof(Fe), st);
         if (rc) return rc;
         uint4* work = (uint4*)c.ws;
         NttPass p{};
@@ -520,7 +518,7 @@ struct Ops {
             }
             if (rc) return rc;
         }
-        return HODOR_OK;
+        return c.ws_release(st);
     }
 
     static int scale_pow(Ctx& c, uint4* a, size_t n, const Fe& g, cudaStream_t st) {
@@ -568,7 +566,7 @@ struct Ops {
         const int levels = (int)m.size() - 1;  // m[levels] == 1
         size_t scratch = 0;
         for (int l = 0; l < levels; l++) scratch += m[l] + m[l + 1];  // running products + totals
-        int rc = c.ensure_workspace((scratch + 1) * sizeof(Fe));
+        int rc = c.ws_acquire((scratch + 1) * sizeof(Fe), st);
         if (rc) return rc;
         uint4* base = (uint4*)c.ws;
         std::vector<uint4*> pre(levels), tot(levels + 1);
@@ -596,7 +594,7 @@ struct Ops {
                                                                              d_status, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
-        return HODOR_OK;
+        return c.ws_release(st);
     }
 
     static int selftest_mul_pre(Ctx& c, unsigned long long* d_mismatch, cudaStream_t st) {
@@ -617,7 +615,7 @@ struct Ops {
         const uint32_t K = n >= ((size_t)1 << 22) ? 128u : (n >= ((size_t)1 << 16) ? 32u : 8u);
         const size_t M = (n + K - 1) / K;
         const unsigned blocks = (unsigned)((M + 255) / 256);
-        int rc = c.ensure_workspace((size_t)blocks * sizeof(Fe));
+        int rc = c.ws_acquire((size_t)blocks * sizeof(Fe), st);
         if (rc) return rc;
         FePre gM;
         f.make_pre(f.pow(g, (uint64_t)M), gM.w, gM.q);
@@ -630,7 +628,7 @@ struct Ops {
             eval_final_kernel<F><<<1, 256, 0, st>>>((const uint4*)c.ws, blocks, d_out, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
-        return HODOR_OK;
+        return c.ws_release(st);
     }
 
     // ------------------------------------------------------------------ Merkle tail, FRI fold
@@ -650,14 +648,15 @@ struct Ops {
                         uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st) {
         // omega_N^-1 of the INITIAL domain (src/fri/fri_on_values.rs:24-25), table over exponents < N/2
         maybe_evict(c);
-        static std::map<uint32_t, Fe> inv_cache;  // guarded by Ctx::mu; a host inversion is ~400 host multiplies
+        auto& inv_cache = c.inv_cache;  // a host inversion is ~400 host multiplies
         Fe omega, omega_inv;
         int rc = h_domain_generator(log_n0, omega);
         if (rc) return fail(rc, "FRI domain larger than the field's 2-adicity");
-        auto cached = inv_cache.find(log_n0);
+        const uint64_t inv_key = ((uint64_t)F::ID << 32) | log_n0;
+        auto cached = inv_cache.find(inv_key);
         if (cached == inv_cache.end()) {
             h_inverse(omega, omega_inv);
-            inv_cache.emplace(log_n0, omega_inv);
+            inv_cache.emplace(inv_key, omega_inv);
         } else {
             omega_inv = cached->second;
         }

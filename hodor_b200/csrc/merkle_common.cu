@@ -96,4 +96,36 @@ int merkle_path_gather(Ctx& c, const uint4* nodes, const uint4* values, size_t s
     return HODOR_OK;
 }
 
+// One block per query: slot q of `out` (66 digests wide) receives the path (leaf-pair hash first, then the
+// siblings bottom-up; src/iop/blake2s_trivial_iop.rs:251-279) in digests [0, 64) and the queried value in
+// digest 64.
+__global__ void merkle_paths_kernel(const uint4* nodes, const uint4* values, size_t size, const uint64_t* indices,
+                                    uint4* out, const __grid_constant__ B2sState key) {
+    const uint32_t j = threadIdx.x;
+    const size_t index = (size_t)indices[blockIdx.x];
+    uint4* slot = out + 2 * 66 * (size_t)blockIdx.x;
+    uint32_t levels = 0;
+    while (((size_t)1 << (levels + 1)) < size) levels++;
+    if (j == 0) {
+        const Digest leaf = ld_digest(values, index ^ 1);
+        st_digest(slot, 0, hash_leaf32(key, leaf.w));
+        st_digest(slot, 64, ld_digest(values, index));
+    }
+    if (j < levels) {
+        const size_t heap = ((size + index) >> (1 + j)) ^ 1;
+        st_digest(slot, 1 + j, ld_digest(nodes, heap));
+    }
+}
+
+int merkle_paths_gather(Ctx& c, const uint4* nodes, const uint4* values, size_t size, const uint64_t* d_indices,
+                        uint32_t count, uint4* out, cudaStream_t st) {
+    if (count == 0) return HODOR_OK;
+    {
+        ProfScope ps(c, st, "merkle_path");
+        merkle_paths_kernel<<<count, 64, 0, st>>>(nodes, values, size, d_indices, out, c.key);
+    }
+    HODOR_CUDA_TRY(cudaGetLastError());
+    return HODOR_OK;
+}
+
 }  // namespace hodor

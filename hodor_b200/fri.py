@@ -13,7 +13,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import field as fld
-from ._ffi import HodorError, SynthesisError, check, ensure_init, last_error, lib, u8p
+from ._ffi import HodorError, SynthesisError, check, ensure_init, last_error, lib, raise_last, u8p
 from .domains import Domain
 from .field import _p
 from .iop import DeviceIOP, TrivialBlake2sIOP, TrivialBlake2sIopQuery, TrivialCombiner
@@ -86,7 +86,13 @@ class FRIProofPrototype:
                 self._values[i] = Polynomial(self.field_id, self._fetch_layer(i + 1, want_values=True)[1], VALUES)
         return self._values  # type: ignore[return-value]
 
+    def _h(self) -> int:
+        if not getattr(self, "_handle", None):
+            raise RuntimeError("the FRIProofPrototype's device memory was freed")
+        return self._handle
+
     def _fetch_layer(self, layer: int, want_nodes: bool = False, want_values: bool = False):
+        self._h()
         size = int(lib.hodor_cuda_fri_layer_size(self._handle, layer))
         nodes = np.zeros((size, 32), np.uint8) if want_nodes else None
         values = np.zeros((size, 4), np.uint64) if want_values else None
@@ -95,6 +101,7 @@ class FRIProofPrototype:
         return nodes, values
 
     def _query(self, layer: int, natural_index: int) -> TrivialBlake2sIopQuery:
+        self._h()
         size = int(lib.hodor_cuda_fri_layer_size(self._handle, layer))
         value = np.zeros(4, np.uint64)
         path = np.zeros((size.bit_length() - 1, 32), np.uint8)
@@ -137,10 +144,7 @@ class NaiveFriIop:
         h = lib.hodor_cuda_fri_commit(lde_values.as_ref().ctypes.data, C.c_uint64(n), lde_factor,
                                       output_coeffs_at_degree_plus_one, 0, lde_values.field_id)
         if not h:
-            msg = last_error()
-            if "2-adicity" in msg:
-                check(-2)
-            raise HodorError(-1 if "fri_commit:" in msg else -3, msg)
+            raise_last()  # the code the library recorded: INVALID_ARG, DOMAIN (-> SynthesisError), OOM, CUDA
         return FRIProofPrototype(lde_values.field_id, h, n, lde_factor, output_coeffs_at_degree_plus_one)
 
     @staticmethod

@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import field as fld
-from ._ffi import check, ensure_init, lib, u8p
+from ._ffi import check, ensure_init, lib, raise_last, u8p, vp
 from .field import _p
 from .polynomials import _as_elems
 
@@ -217,7 +217,7 @@ class TrivialBlake2sIOP:
         return TrivialBlake2sIopQuery(natural_index, leafs[natural_index].copy(), self.tree.get_path(tree_index, leafs))
 
     def __eq__(self, other) -> bool:  # :336-340: equality is equality of roots
-        return isinstance(other, (TrivialBlake2sIOP, DeviceIOP)) and self.get_root() == other.get_root()
+        return hasattr(other, "get_root") and self.get_root() == other.get_root()
 
 
 class DeviceIOP:
@@ -261,3 +261,137 @@ class DeviceIOP:
 
     def __eq__(self, other) -> bool:
         return isinstance(other, (TrivialBlake2sIOP, DeviceIOP)) and self.get_root() == other.get_root()
+
+
+class CommittedOracle:
+    """`I::create(lde.as_ref())` with the leaves and the tree resident in HBM behind a `hodor_tree`
+    handle -- the oracle a prover keeps per register between the commit phase and the query phase
+    (src/prover/mod.rs:73-95 and :142-151).  Same surface as TrivialBlake2sIOP; `query` extracts the
+    value and the authentication path on the device (log2(n) digests cross PCIe, not the tree)."""
+
+    def __init__(self, field_id: int, handle: int, root: bytes):
+        self.field_id = field_id
+        self._handle = handle
+        self._root = bytes(root)
+        self._size = int(lib.hodor_cuda_tree_size(handle))
+        self._keepalive = None
+
+    # ---- constructors ---------------------------------------------------------------------------
+    @staticmethod
+    def create(field_id: int, leafs) -> "CommittedOracle":
+        """IOP::create on host values (copied in once, then owned by the handle)."""
+        leafs = _as_elems(leafs)
+        n = leafs.shape[0]
+        if n < 2 or n & (n - 1):
+            raise AssertionError("assert!(num_leafs == num_leafs.next_power_of_two())")
+        ensure_init()
+        root = np.zeros(32, np.uint8)
+        h = lib.hodor_cuda_tree_commit(leafs.ctypes.data, C.c_uint64(n), 0, root.ctypes.data_as(u8p), field_id)
+        if not h:
+            raise_last()
+        return CommittedOracle(field_id, h, root.tobytes())
+
+    @staticmethod
+    def create_on_device(field_id: int, d_values) -> "CommittedOracle":
+        """IOP::create on a device-resident vector (torch tensor (n, 4) int64); the tensor is borrowed."""
+        n = int(d_values.shape[0])
+        if n < 2 or n & (n - 1):
+            raise AssertionError("assert!(num_leafs == num_leafs.next_power_of_two())")
+        ensure_init()
+        import torch
+        torch.cuda.current_stream().synchronize()  # the commit runs on the library's stream
+        root = np.zeros(32, np.uint8)
+        h = lib.hodor_cuda_tree_commit(d_values.data_ptr(), C.c_uint64(n), 1, root.ctypes.data_as(u8p), field_id)
+        if not h:
+            raise_last()
+        o = CommittedOracle(field_id, h, root.tobytes())
+        o._keepalive = d_values
+        return o
+
+    @staticmethod
+    def lde_commit_batch(polys: Sequence, factor: int, coset: bool = False) -> List["CommittedOracle"]:
+        """`for w in witness { let lde = w.lde(..)?; I::create(lde.as_ref()) }` in one pipelined call."""
+        from .polynomials import COEFFICIENTS
+        if not polys:
+            return []
+        if factor < 1 or factor & (factor - 1):
+            raise AssertionError("assert!(factor.is_power_of_two())")
+        fid, exp = polys[0].field_id, polys[0].exp
+        for p in polys:
+            if p.form != COEFFICIENTS:
+                raise TypeError("lde needs Polynomial<F, Coefficients>")
+            if p.field_id != fid or p.exp != exp:
+                raise ValueError("lde_commit_batch: polynomials must share field and size")
+        ensure_init()
+        count = len(polys)
+        ins = (vp * count)(*[p.as_ref().ctypes.data for p in polys])
+        outs = (vp * count)()
+        roots = np.zeros((count, 32), np.uint8)
+        check(lib.hodor_cuda_lde_commit_batch(ins, count, exp, factor.bit_length() - 1, int(coset), 0, outs,
+                                              roots.ctypes.data_as(u8p), fid))
+        return [CommittedOracle(fid, outs[i], roots[i].tobytes()) for i in range(count)]
+
+    @staticmethod
+    def lde_commit(poly, factor: int, coset: bool = False) -> "CommittedOracle":
+        return CommittedOracle.lde_commit_batch([poly], factor, coset)[0]
+
+    # ---- lifetime --------------------------------------------------------------------------------
+    def free(self) -> None:
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            lib.hodor_cuda_tree_free(h)
+
+    def __del__(self):
+        self.free()
+
+    def _h(self) -> int:
+        if not self._handle:
+            raise RuntimeError("this CommittedOracle's device memory was freed")
+        return self._handle
+
+    # ---- IOP surface -----------------------------------------------------------------------------
+    def size(self) -> int:
+        return self._size
+
+    def get_root(self) -> bytes:
+        return self._root
+
+    def get_challenge_scalar_from_root(self) -> np.ndarray:
+        out = np.zeros(4, np.uint64)
+        check(lib.hodor_cuda_tree_root(self._h(), None, _p(out)))  # computed on the device with the root
+        return out
+
+    def device_values_ptr(self) -> int:
+        return int(lib.hodor_cuda_tree_values(self._h()))
+
+    def values(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self._size - first if count is None else count
+        out = np.zeros((count, 4), np.uint64)
+        check(lib.hodor_cuda_tree_read(self._h(), C.c_uint64(first), C.c_uint64(count), _p(out), None))
+        return out
+
+    @property
+    def nodes(self) -> np.ndarray:
+        out = np.zeros((self._size, 32), np.uint8)
+        check(lib.hodor_cuda_tree_read(self._h(), C.c_uint64(0), C.c_uint64(self._size), None, out.ctypes.data_as(u8p)))
+        return out
+
+    def query(self, natural_index: int, leafs=None) -> TrivialBlake2sIopQuery:
+        return self.query_batch([natural_index])[0]
+
+    def query_batch(self, natural_indices: Sequence[int]) -> List[TrivialBlake2sIopQuery]:
+        for i in natural_indices:
+            assert 0 <= i < self._size  # reference: assert!(natural_index < self.tree.size())
+        k = len(natural_indices)
+        depth = self._size.bit_length() - 1
+        idx = np.asarray(list(natural_indices), dtype=np.uint64)
+        values = np.zeros((k, 4), np.uint64)
+        paths = np.zeros((k, depth, 32), np.uint8)
+        n = check(lib.hodor_cuda_tree_query_batch(self._h(), _p(idx) if k else None, k, _p(values), paths.ctypes.data_as(u8p)))
+        assert n == depth
+        return [TrivialBlake2sIopQuery(int(idx[i]), values[i].copy(), [d.tobytes() for d in paths[i]]) for i in range(k)]
+
+    verify_query = staticmethod(TrivialBlake2sIOP.verify_query)
+
+    def __eq__(self, other) -> bool:
+        return hasattr(other, "get_root") and self.get_root() == other.get_root()

@@ -51,6 +51,8 @@ int hodor_cuda_device_count(void);
 int hodor_cuda_init(int device);
 void hodor_cuda_shutdown(void);
 const char* hodor_cuda_last_error(void);
+/* the HODOR_ERR_* code that goes with hodor_cuda_last_error() (for entry points that return a handle or NULL) */
+int hodor_cuda_last_error_code(void);
 /* bytes of device workspace + cached twiddle tables currently held */
 size_t hodor_cuda_workspace_bytes(void);
 
@@ -137,6 +139,39 @@ int hodor_cuda_evaluate_at(const uint64_t* coeffs, uint64_t n, const uint64_t g[
 /* Blake2sIopTree::create (src/iop/blake2s_trivial_iop.rs:131-219).  n a power of two >= 2;
  * nodes receives n * 32 bytes. */
 int hodor_cuda_merkle_build(const uint64_t* leaves, uint64_t n, uint8_t* nodes, int field_id);
+
+/* ---- committed oracles: values + Merkle tree resident in HBM ------------------------------------ */
+/* What Prover::prove does with every register and with g (src/prover/mod.rs:73-80, :91-95):
+ *     let lde = w.lde(&worker, lde_factor)?;  let oracle = I::create(lde.as_ref());
+ * in one call: coefficients in (host or device), the LDE and the tree stay on the device behind the handle,
+ * only the root (32 B) comes back.  The handle serves IOP::query (src/iop/blake2s_trivial_iop.rs:251-279,
+ * :324-338) without ever moving the 2n * 32 bytes of values and nodes over PCIe. */
+typedef struct hodor_tree hodor_tree;
+hodor_tree* hodor_cuda_lde_commit(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, int coset,
+                                  int coeffs_on_device, uint8_t root[32], int field_id);
+/* The register loop of the prover: `count` polynomials of one shape; the host->device copy of polynomial
+ * i+1 overlaps the LDE + tree build of polynomial i (pinned host memory needed for the overlap).
+ * trees[i] receives the handles, roots (may be NULL) count * 32 bytes. */
+int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, uint32_t log_n, uint32_t log_factor,
+                                int coset, int coeffs_on_device, hodor_tree** trees, uint8_t* roots, int field_id);
+/* IopTree::create / IOP::create (src/iop/blake2s_trivial_iop.rs:131-219, :291-297) on n values.  Host values
+ * are copied in and owned by the handle; device values are borrowed (keep them alive until _free). */
+hodor_tree* hodor_cuda_tree_commit(const uint64_t* values, uint64_t n, int values_on_device, uint8_t root[32],
+                                   int field_id);
+void hodor_cuda_tree_free(hodor_tree* t);
+uint64_t hodor_cuda_tree_size(const hodor_tree* t);
+/* device pointers of the committed values (n * 32 B, natural order) and of `nodes` (n * 32 B, heap order):
+ * inputs for hodor_cuda_fri_commit(lde_on_device = 1) and the other `_dev` entry points */
+const void* hodor_cuda_tree_values(const hodor_tree* t);
+const void* hodor_cuda_tree_nodes(const hodor_tree* t);
+/* get_root (:221-224) and get_challenge_scalar_from_root (:230-234); either pointer may be NULL */
+int hodor_cuda_tree_root(const hodor_tree* t, uint8_t root[32], uint64_t challenge[4]);
+/* IOP::query: value (4 u64) and path (log2(n) * 32 B, leaf-pair hash first).  Returns the path length. */
+int hodor_cuda_tree_query(const hodor_tree* t, uint64_t natural_index, uint64_t value[4], uint8_t* path);
+int hodor_cuda_tree_query_batch(const hodor_tree* t, const uint64_t* natural_indices, uint32_t count, uint64_t* values,
+                                uint8_t* paths);
+/* copies values[first, first+count) and / or nodes[first, first+count) to the host (either may be NULL) */
+int hodor_cuda_tree_read(const hodor_tree* t, uint64_t first, uint64_t count, uint64_t* values, uint8_t* nodes);
 
 /* ---- FRI commit chain ---------------------------------------------------------------------- */
 /* NaiveFriIop::proof_from_lde_by_values (src/fri/fri_on_values.rs:11-159), result kept on the

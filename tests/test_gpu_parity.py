@@ -689,3 +689,148 @@ def test_sharded_fri_world1_equals_single_gpu_chain(hodor, oracle):
     assert proto.roots == want.roots() and len(proto.commitments) >= 5
     assert np.array_equal(np.stack(proto.challenges), want.challenges)
     assert np.array_equal(proto.final_coefficients, want.final_coefficients)
+
+
+# ----------------------------------------------------------------------------------------------
+# committed oracles (values + tree resident in HBM), concurrency, pageable memory
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
+def test_committed_oracle_matches_oracle(hodor, oracle, fid):
+    """hodor_cuda_tree_commit / _query against Blake2sIopTree::create + get_path of the oracle."""
+    for log_n in (1, 2, 5, 10, 11, 14):
+        n = 1 << log_n
+        vals = oracle.random_elements(fid, n, seed=300 + log_n)
+        nodes = oracle.merkle_create(fid, vals)
+        orc = hodor.CommittedOracle.create(fid, vals)
+        assert orc.size() == n and orc.get_root() == nodes[1].tobytes()
+        assert np.array_equal(orc.nodes, nodes) and np.array_equal(orc.values(), vals)
+        assert np.array_equal(orc.get_challenge_scalar_from_root(), oracle.interpret_hash(fid, nodes[1].tobytes()))
+        idx = sorted({0, n - 1, n // 2, *[int(x) for x in np.random.default_rng(log_n).integers(0, n, 70)]})
+        qs = orc.query_batch(idx)  # more than one launch's worth of slots when n is large
+        for i, q in zip(idx, qs):
+            assert q.natural_index() == i and np.array_equal(q.value(), vals[i])
+            assert q.path() == oracle.merkle_path(fid, nodes, vals, i)
+            assert hodor.TrivialBlake2sIOP.verify_query(q, orc.get_root())
+        assert orc.query(idx[-1]) == qs[-1]
+        assert orc == hodor.TrivialBlake2sIOP.create(fid, vals)
+        orc.free()
+        with pytest.raises(RuntimeError):
+            orc.query(0)
+    with pytest.raises(AssertionError):
+        hodor.CommittedOracle.create(fid, oracle.random_elements(fid, 48, 1))
+
+
+def test_lde_commit_batch_matches_separate_calls(hodor, oracle):
+    """The register loop of Prover::prove (src/prover/mod.rs:73-80): lde then I::create, pipelined."""
+    import torch
+    from hodor_b200 import device as dev
+    fid, log_n, L = 0, 13, 8
+    polys = [oracle.random_elements(fid, 1 << log_n, seed=80 + i) for i in range(5)]
+    for coset in (False, True):
+        for count in (0, 1, 2, 5):
+            got = hodor.CommittedOracle.lde_commit_batch([hodor.Polynomial.from_coeffs(fid, a) for a in polys[:count]], L, coset)
+            assert len(got) == count
+            for a, o in zip(polys, got):
+                lde = oracle.lde(fid, a, log_n, L, coset)
+                assert np.array_equal(o.values(), lde)
+                assert np.array_equal(o.nodes, oracle.merkle_create(fid, lde))
+                o.free()
+    # FRI straight off a committed oracle's device-resident values (no host copy of the LDE)
+    a = oracle.random_elements(fid, 1 << 12, seed=91)
+    orc = hodor.CommittedOracle.lde_commit(hodor.Polynomial.from_coeffs(fid, a), L, True)
+    lde = oracle.lde(fid, a, 12, L, True)
+    from hodor_b200 import _ffi
+    h = _ffi.lib.hodor_cuda_fri_commit(orc.device_values_ptr(), C.c_uint64(orc.size()), L, 1, 1, fid)
+    assert h, _ffi.last_error()
+    proto = hodor.FRIProofPrototype(fid, h, orc.size(), L, 1)
+    want = oracle.fri_commit(fid, lde, L, 1)
+    assert proto.get_roots() == want.roots() and proto.get_roots()[0] == orc.get_root()
+    assert np.array_equal(proto.final_coefficients, want.final_coefficients)
+    proto.free()
+    orc.free()
+    # device-resident coefficients in, and IOP::create on a borrowed device vector
+    d = dev.to_device(a)
+    out = (C.c_void_p * 1)()
+    roots = np.zeros(32, np.uint8)
+    ins = (C.c_void_p * 1)(d.data_ptr())
+    torch.cuda.synchronize()
+    _ffi.check(_ffi.lib.hodor_cuda_lde_commit_batch(ins, 1, 12, 3, 1, 1, out, roots.ctypes.data_as(_ffi.u8p), fid))
+    assert roots.tobytes() == want.roots()[0]
+    _ffi.lib.hodor_cuda_tree_free(out[0])
+    o2 = hodor.CommittedOracle.create_on_device(fid, dev.to_device(lde))
+    assert o2.get_root() == want.roots()[0]
+    o2.free()
+    with pytest.raises(hodor.SynthesisError):  # Domain::new_for_size -> Err past the 2-adicity (BN254: S = 28)
+        hodor.CommittedOracle.lde_commit(hodor.Polynomial.from_coeffs(1, oracle.random_elements(1, 1 << 12, 3)), 1 << 17)
+
+
+def test_c_abi_from_four_host_threads(hodor, oracle):
+    """The reference calls its transforms from inside spawned threads (src/polynomials/mod.rs:446-459) and
+    `create` makes its own Worker (src/iop/blake2s_trivial_iop.rs:147).  Four host threads hammer the host-pointer
+    ABI (transform, Merkle build, FRI commit, committed oracle) concurrently; every result is bit-exact and the
+    calls do not deadlock."""
+    import threading
+    fid = 0
+    a = [oracle.random_elements(fid, 1 << 14, seed=500 + t) for t in range(4)]
+    want_lde = [oracle.lde(fid, x, 14, 4, True) for x in a]
+    want_nodes = [oracle.merkle_create(fid, x) for x in a]
+    want_fri = [oracle.fri_commit(fid, x, 4, 1) for x in a]
+    errors = []
+
+    def work(t):
+        try:
+            for rep in range(6):
+                got = hodor.Polynomial.from_coeffs(fid, a[t]).coset_lde(hodor.Worker(), 4).as_ref()
+                assert np.array_equal(got, want_lde[t]), ("lde", t, rep)
+                tree = hodor.Blake2sIopTree.create(fid, a[t])
+                assert np.array_equal(tree.nodes, want_nodes[t]), ("merkle", t, rep)
+                proto = hodor.NaiveFriIop.proof_from_lde(hodor.Polynomial.from_values(fid, a[t]), 4, 1, None)
+                assert proto.get_roots() == want_fri[t].roots(), ("fri", t, rep)
+                proto.free()
+                orc = hodor.CommittedOracle.lde_commit(hodor.Polynomial.from_coeffs(fid, a[t]), 4, True)
+                assert orc.get_root() == oracle.merkle_create(fid, want_lde[t])[1].tobytes(), ("commit", t, rep)
+                orc.free()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+        assert not th.is_alive(), "deadlock: a thread is still inside the C ABI"
+    assert not errors, errors
+
+
+def test_dev_calls_on_two_streams_share_the_workspace_safely(hodor, oracle):
+    """`_dev` entry points enqueue on the caller's stream and share one context workspace; calls issued
+    back to back on two different streams must not overwrite each other's inter-pass data."""
+    import torch
+    from hodor_b200 import device as dev
+    fid, log_n = 0, 16
+    xs = [oracle.random_elements(fid, 1 << log_n, seed=600 + i) for i in range(4)]
+    omega = oracle.domain_generator(fid, log_n)
+    want = [oracle.best_fft(fid, x, omega, log_n) for x in xs]
+    d_in = [dev.to_device(x) for x in xs]
+    d_out = [dev.empty_elems(1 << log_n) for _ in xs]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(4):
+            with torch.cuda.stream(streams[i % 2]):
+                dev.fft(d_in[i], d_out[i], log_n, False, fid)
+        torch.cuda.synchronize()
+        for i in range(4):
+            assert np.array_equal(dev.to_host(d_out[i]), want[i]), (rep, i)
+
+
+def test_pageable_host_memory_is_accepted(hodor, oracle):
+    """A Rust `Vec<F>` is pageable: the host-pointer entry points must give the same bits from plain numpy
+    buffers (no pinning) as from pinned ones."""
+    from hodor_b200 import _ffi
+    from hodor_b200.field import _p
+    fid, log_n, log_f = 0, 16, 2
+    a = oracle.random_elements(fid, 1 << log_n, seed=77)
+    out = np.zeros(((1 << log_n) << log_f, 4), np.uint64)
+    _ffi.check(_ffi.lib.hodor_cuda_lde(_p(a), log_n, log_f, 1, _p(out), fid))
+    assert np.array_equal(out, oracle.lde(fid, a, log_n, 1 << log_f, True))
