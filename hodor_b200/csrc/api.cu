@@ -270,6 +270,7 @@ int hodor_cuda_init(int device) {
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaMalloc((void**)&c->small, 4096));
+    HODOR_CUDA_TRY(cudaHostAlloc((void**)&c->pinned_small, Ctx::PINNED_SMALL_BYTES, cudaHostAllocDefault));
     c->key = b2s_keyed_state();
     if (const char* mb = getenv("HODOR_TABLE_BUDGET_MB")) c->full_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
     if (const char* mb = getenv("HODOR_POOL_CACHE_MB")) c->pool_cache_cap = (size_t)strtoull(mb, nullptr, 10) << 20;
@@ -300,6 +301,7 @@ void hodor_cuda_shutdown(void) {
     for (auto e : g_ctx->event_pool) cudaEventDestroy(e);
     if (g_ctx->ws_event) cudaEventDestroy(g_ctx->ws_event);
     cudaFree(g_ctx->small);
+    if (g_ctx->pinned_small) cudaFreeHost(g_ctx->pinned_small);
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_in);
     cudaStreamDestroy(g_ctx->copy_out);
@@ -926,6 +928,7 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
         cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming);
     }
+    const bool roots_pinned = roots != nullptr && (size_t)count * 32 <= Ctx::PINNED_SMALL_BYTES;
     auto step = [&](uint32_t i) -> int {
         hodor_tree* t = tree_alloc(c, field_id, total, true);
         if (!t) return HODOR_ERR_OOM;
@@ -944,7 +947,10 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
         if (!coeffs_on_device) HODOR_CUDA_TRY(cudaEventRecord(comp_done[i % nbuf], c->stream));
         r = do_merkle(*c, ops, t->values, total, t->nodes, t->root, t->chal, c->stream);
         if (r) return r;
-        if (roots) HODOR_CUDA_TRY(cudaMemcpyAsync(roots + 32 * (size_t)i, t->root, 32, cudaMemcpyDeviceToHost, c->stream));
+        if (roots) {  // via pinned scratch while it lasts: see Ctx::pinned_small
+            uint8_t* dst = roots_pinned ? c->pinned_small + 32 * (size_t)i : roots + 32 * (size_t)i;
+            HODOR_CUDA_TRY(cudaMemcpyAsync(dst, t->root, 32, cudaMemcpyDeviceToHost, c->stream));
+        }
         return HODOR_OK;
     };
     for (uint32_t i = 0; i < count && rc == HODOR_OK; i++) rc = step(i);
@@ -956,6 +962,7 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
         if (in_buf[b]) c->pool_free(in_buf[b]);
     }
     if (rc == HODOR_OK && e != cudaSuccess) rc = cuda_fail(e, "lde_commit");
+    if (rc == HODOR_OK && roots_pinned) memcpy(roots, c->pinned_small, (size_t)count * 32);
     if (rc) {
         for (uint32_t i = 0; i < count; i++) {
             tree_destroy(trees[i]);

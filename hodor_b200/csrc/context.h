@@ -62,6 +62,11 @@ struct Ctx {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     uint4* small = nullptr;  // 4 KiB of device scratch for scalars
+    // Pinned host scratch for small results (roots) of pipelined entry points: a device-to-host copy into the
+    // caller's pageable memory blocks the calling thread until the stream has drained, which would serialise
+    // the pipeline; results land here asynchronously and are handed over after the final synchronise.
+    uint8_t* pinned_small = nullptr;
+    static constexpr size_t PINNED_SMALL_BYTES = 64 << 10;
     B2sState key;
     std::map<std::string, NttTables> ntt_tables;
     std::map<std::string, PowTables> pow_tables;

@@ -58,10 +58,14 @@ struct BlsFr {  // what the reference's src/bn256.rs declares: the BLS12-381 sca
     HD static constexpr uint32_t NP(int i) { return i == 0 ? 0u - P(0) : ~P(i); }  // 2^256 - p (p odd)
 };
 
-struct Bn254Fr {  // the field usually called "bn256 Fr" (not what src/bn256.rs holds)
+// The field usually called "bn256 Fr" (not what src/bn256.rs holds).  GENERATOR = 7 is the declaration of the Rust
+// types a matter-labs caller links for this field (pairing_ce / bellman_ce `bn256::Fr`: PrimeFieldGenerator = "7";
+// halo2curves' bn256 Fr uses 7 as well and publishes the resulting ROOT_OF_UNITY, pinned in tests/test_oracle_pins.py),
+// so multiplicative_generator(), root_of_unity(), every domain generator and coset shift are bit-compatible with them.
+struct Bn254Fr {
     static constexpr int ID = FIELD_BN254_FR;
     static constexpr uint32_t INV = 0xefffffffu;
-    static constexpr int S = 28, NUM_BITS = 254, GENERATOR = 5;
+    static constexpr int S = 28, NUM_BITS = 254, GENERATOR = 7;
     HD static constexpr uint32_t P(int i) {
         constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                                    0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};

@@ -48,7 +48,7 @@ static const uint64_t MODULI[NUM_FIELDS][4] = {
     {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
     {0x0000000000000001ULL, 0x0000000000000000ULL, 0x0000000000000000ULL, 0x0800000000000011ULL},
 };
-static const uint64_t GENERATORS[NUM_FIELDS] = {7, 5, 3};
+static const uint64_t GENERATORS[NUM_FIELDS] = {7, 7, 3};  /* BN254: pairing_ce / ff_ce bn256::Fr declares 7 */
 
 static field_t FIELDS[NUM_FIELDS];
 static pthread_once_t fields_once = PTHREAD_ONCE_INIT;

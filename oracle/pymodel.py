@@ -90,7 +90,7 @@ BLS12_381_FR = Field(  # this is what src/bn256.rs actually declares
 BN254_FR = Field(
     "bn254_fr",
     21888242871839275222246405745257275088548364400416034343698204186575808495617,
-    5,
+    7,  # PrimeFieldGenerator of pairing_ce's bn256::Fr (the reference itself does not declare this field)
     4,
 )
 STARK252 = Field(
