@@ -542,47 +542,126 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     del h_in
     os.sched_setaffinity(0, all_cpus)
 
-    # ---- the sharded four-step NTT (only path with a collective), N > 1
-    sharded = None
-    if world > 1:
-        from hodor_b200.sharded import ntt_sharded
-        from hodor_b200 import field as fld
-        sharded = []
-        for ln in ([24, 26, 28] if not args.sweep else list(range(18, 29, 2))):
-            m = (1 << ln) // world
-            local = dev.to_device(synthetic_elements(m, seed=3000 + rank))
-            omega = H.Domain.new_for_size(FIELD, 1 << ln).generator
-            ms = timed(lambda: ntt_sharded(local, ln, omega, FIELD), max(2, args.steps // 2), 2) / max(2, args.steps // 2)
-            sharded.append({"log_n": ln, "ms": ms, "value": (1 << ln) / (ms * 1e-3), "unit": "field-elems/s",
-                            "hbm_frac_aggregate": 64 * (1 << ln) / (ms * 1e-3) / 1e9 / (peak_gbs * world)})
-            del local
+    # ---- the paths with a real exchange step, through the C ABI (hodor_cuda_ntt_sharded / _lde_fri_sharded:
+    # NCCL send/recv issued by the library), at EVERY N including 1, each checked against the single-GPU result
+    from hodor_b200 import multigpu as mg
+    mg.comm_init()
+
+    def device_elements(count, seed, start=0, step=1):
+        """Deterministic canonical elements made on the device: element j depends on its global index only, so
+        every rank can build its own slice (start + step * t) of one shared vector without host traffic."""
+        idx = start + step * torch.arange(count, dtype=torch.int64, device="cuda")
+        out = torch.empty((count, 4), dtype=torch.int64, device="cuda")
+        for limb, mul in enumerate((0x2545F4914F6CDD1D, 0x5851F42D4C957F2D, 0x14057B7EF767814F, 0x27BB2EE687B0B0FD)):
+            x = (idx + (seed + 1) * 0x632BE59BD9B4E019) * mul
+            x ^= (x >> 29)
+            out[:, limb] = x * 0x369DEA0F31A53F85
+        out[:, 3] &= 0x3FFFFFFFFFFFFFFF  # top limb < 2^62 < the modulus' top limb: canonical
+        return out
+
+    def timed_max(fn, reps):
+        fn()
+        best = None
+        for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            best = ms if best is None else min(best, ms)
+        return best
+
+    log_g = world.bit_length() - 1
+    sharded = []
+    sizes = [24, 26, 28] if not args.sweep else list(range(18, 29, 2))
+    for ln in sizes:
+        nn = 1 << ln
+        m = nn >> log_g
+        omega = H.Domain.new_for_size(FIELD, nn).generator
+        local = device_elements(m, ln, start=rank, step=world)  # cyclic slice a[j * G + rank]
+        out = dev.empty_elems(m)
+        ms = timed_max(lambda: mg.ntt_sharded(local, ln, omega, FIELD, out), 3)
+        row = {"log_n": ln, "ms": ms, "value": nn / (ms * 1e-3), "unit": "field-elems/s",
+               "hbm_frac_aggregate": 64 * nn / (ms * 1e-3) / 1e9 / (peak_gbs * world)}
+        # parity + the single-GPU time of the same transform, on rank 0 (its own share of the output: the
+        # rank-th n/G^2 chunk of every n/G block; every rank's share at sizes <= 2^24 via gather)
+        if world > 1:
+            mg.ntt_sharded(local, ln, omega, FIELD, out)
+            ok = torch.ones(1, dtype=torch.int64, device="cuda")
+            if rank == 0:
+                full = device_elements(nn, ln)
+                ref = dev.empty_elems(nn)
+                t1 = timed(lambda: dev.fft(full, ref, ln, False, FIELD), 3, 1) / 3
+                del full
+                chunk = m >> log_g
+                mine = ref.view(world, world, chunk, 4)[:, 0].reshape(m, 4)  # A[k2 * m + 0 * chunk + k]
+                good = bool(torch.equal(mine, out))
+                row["single_gpu_ms"] = t1
+                row["strong_efficiency"] = t1 / (world * ms)
+            if ln <= 24:
+                parts = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+                dist.gather(out, parts, dst=0)
+                if rank == 0:
+                    for h in range(world):
+                        good = good and bool(torch.equal(ref.view(world, world, m >> log_g, 4)[:, h].reshape(m, 4), parts[h]))
+                    row["checked"] = "every rank's output == single-GPU NTT (gathered)"
+                    del parts
+            elif rank == 0:
+                row["checked"] = "rank 0's output share == single-GPU NTT"
+            if rank == 0:
+                row["matches_single_gpu"] = good
+                del ref
+        else:
+            row["matches_single_gpu"] = True  # world 1: the same kernels, nothing exchanged
+            row["strong_efficiency"] = 1.0
+        sharded.append(row)
+        del local, out
+        torch.cuda.empty_cache()
 
     # ---- the north-star target: ONE 2^24 -> 2^28 coset LDE + full FRI commit chain over all ranks
-    # (cosets sharded with no communication; one NCCL all-to-all per committed FRI layer)
-    sharded_fri = None
-    if world > 1 and world <= 16:
-        from hodor_b200.sharded_fri import fri_commit_sharded, lde_sharded
-        s_log_f = 4
-        d_shared = dev.to_device(synthetic_elements(n, seed=4000))  # replicated coefficient vector
+    s_log_f = 4
+    d_shared = device_elements(n, 4000)  # replicated coefficient vector
 
-        def lde_fri():
-            loc = lde_sharded(d_shared, LOG_N, s_log_f, True, FIELD)
-            return fri_commit_sharded(loc, n << s_log_f, 1 << s_log_f, 1, FIELD, keep_layers=False)
+    def lde_fri():
+        return mg.lde_fri_sharded(d_shared, LOG_N, s_log_f, True, 1, FIELD)
 
-        lde_fri()
-        barrier()
-        t0 = time.perf_counter()
-        reps = max(2, args.steps // 2)
-        for _ in range(reps):
-            pr = lde_fri()
+    res = lde_fri()
+    barrier()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = lde_fri()
+    torch.cuda.synchronize()
+    s_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / reps
+    sharded_fri = {"workload": f"coset LDE 2^{LOG_N} -> 2^{LOG_N + s_log_f} + FRI commit chain ({len(res[1])} layers, "
+                               f"{len(res[1]) + 1} Merkle trees) sharded over {world} GPU(s)", "ms": s_ms,
+                   "lde_elems_per_s": (n << s_log_f) / (s_ms * 1e-3), "scaling": "strong",
+                   "api": "hodor_cuda_lde_fri_sharded (C ABI; NCCL send/recv per committed layer + 32-byte all-gather of sub-roots)",
+                   "nccl_payload_bytes_per_rank": None,
+                   "timer": "host perf_counter around the synchronous C-ABI call, barrier + synchronize both sides, max over ranks"}
+    b0 = mg.bytes_sent()
+    lde_fri()
+    sharded_fri["nccl_payload_bytes_per_rank"] = mg.bytes_sent() - b0
+    if rank == 0:
+        # the same polynomial through the single-GPU entry points
+        full = dev.empty_elems(n << s_log_f)
+        dev.lde(d_shared, LOG_N, s_log_f, True, full, FIELD)
         torch.cuda.synchronize()
-        s_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / reps
-        sharded_fri = {"workload": f"coset LDE 2^{LOG_N} -> 2^{LOG_N + s_log_f} + FRI commit chain ({pr.num_steps} layers, "
-                                   f"{pr.num_steps + 1} Merkle trees) sharded over {world} GPUs", "ms": s_ms,
-                       "lde_elems_per_s": (n << s_log_f) / (s_ms * 1e-3), "scaling": "strong",
-                       "collective": "NCCL all_to_all_single per committed layer (cyclic -> block), all_gather of sub-roots",
-                       "timer": "host perf_counter, barrier + synchronize both sides, max over ranks"}
-        del d_shared
+        t0 = time.perf_counter()
+        dev.lde(d_shared, LOG_N, s_log_f, True, full, FIELD)
+        ref = dev.fri_commit(full, 1 << s_log_f, 1, FIELD)
+        torch.cuda.synchronize()
+        one_ms = (time.perf_counter() - t0) * 1e3
+        sharded_fri["matches_single_gpu"] = bool(res[0] == ref.get_roots() and np.array_equal(res[1], ref.challenges)
+                                                 and np.array_equal(res[2], ref.final_coefficients))
+        sharded_fri["single_gpu_ms"] = one_ms
+        sharded_fri["strong_efficiency"] = one_ms / (world * s_ms)
+        ref.free()
+        del full
+    del d_shared
+    torch.cuda.empty_cache()
 
     # ---- configs[4], single-GPU column: forward NTT 2^18 .. 2^28 (the sharded columns are `sharded_ntt`)
     sweep = None
@@ -637,10 +716,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "ntt": ntt, "fri": fri,
         }
-        if sharded is not None:
-            line["sharded_ntt"] = {"collective": "NCCL all_to_all_single (one transpose)", "scaling": "strong", "sizes": sharded}
-        if sharded_fri is not None:
-            line["sharded_lde_fri"] = sharded_fri
+        line["sharded_ntt"] = {"api": "hodor_cuda_ntt_sharded (C ABI; four-step, one NCCL all-to-all issued by the library)",
+                               "scaling": "strong", "sizes": sharded}
+        line["sharded_lde_fri"] = sharded_fri
         if sweep is not None:
             line["ntt_sweep"] = sweep
         emit(line)

@@ -208,11 +208,11 @@ static int do_lde(Ctx& c, const FieldOps* ops, const uint4* in, uint4* out, uint
     const Fe shift0 = coset ? gen : one;
     return ops->ntt(c, in, out, log_n, log_f, omega, &shift0, &coset_omega, 0, nullptr, st);
 }
-static int do_merkle(Ctx& c, const FieldOps* ops, const uint4* leaves, size_t n, uint4* nodes, uint4* root, uint4* chal,
-                     cudaStream_t st) {
+int do_merkle(Ctx& c, const FieldOps* ops, const uint4* leaves, size_t n, uint4* nodes, uint4* root, uint4* chal,
+              cudaStream_t st, uint32_t leaf_log_g, size_t leaf_chunk) {
     if (!is_pow2(n) || n < 2) return fail(HODOR_ERR_INVALID_ARG, "merkle: leaf count must be a power of two >= 2");
     size_t w = 0;
-    int rc = merkle_levels(c, leaves, n, nodes, &w, st);
+    int rc = merkle_levels(c, leaves, n, nodes, &w, st, leaf_log_g, leaf_chunk);
     if (rc) return rc;
     if (w == 0) return ops->merkle_tail(c, leaves, nodes, (uint32_t)n, true, root, chal, st);
     return ops->merkle_tail(c, nodes, nodes, (uint32_t)w, false, root, chal, st);
@@ -221,14 +221,6 @@ static int do_merkle(Ctx& c, const FieldOps* ops, const uint4* leaves, size_t n,
 }  // namespace hodor
 
 using namespace hodor;
-
-#define LOCKED_CTX()                          \
-    Ctx* c = ctx();                           \
-    if (!c) return HODOR_ERR_CUDA;            \
-    std::lock_guard<std::mutex> _lk(c->mu)
-#define GET_OPS(field_id)                         \
-    const FieldOps* ops = field_ops(field_id);    \
-    if (!ops) return HODOR_ERR_INVALID_ARG
 
 extern "C" {
 
@@ -283,6 +275,7 @@ void hodor_cuda_shutdown(void) {
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaDeviceSynchronize();
+    comm_destroy(g_ctx);
     for (auto& kv : g_ctx->pow_tables) cudaFree(kv.second.block);
     for (auto& kv : g_ctx->ntt_tables) {
         cudaFree(kv.second.pw.block);
@@ -506,6 +499,15 @@ int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes,
     GET_OPS(field_id);
     return do_merkle(*c, ops, (const uint4*)d_leaves, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,
                      pick_stream(c, stream));
+}
+int hodor_cuda_merkle_build_shard_dev(const void* d_chunks, uint64_t n, uint32_t log_g, void* d_nodes, void* d_root,
+                                      void* d_challenge, int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_g > 4 || !is_pow2(n) || (n >> log_g) <= 1024)
+        return fail(HODOR_ERR_INVALID_ARG, "merkle_build_shard: need log_g <= 4 and more than 1024 leaves per chunk");
+    return do_merkle(*c, ops, (const uint4*)d_chunks, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,
+                     pick_stream(c, stream), log_g, n >> log_g);
 }
 int hodor_cuda_merkle_top_dev(void* d_nodes, uint64_t w, void* d_root, void* d_challenge, int field_id, void* stream) {
     LOCKED_CTX();
@@ -1088,35 +1090,31 @@ int hodor_cuda_profile_end(char* json_out, size_t cap) {
 }
 
 // ---- FRI commit chain --------------------------------------------------------------------------------
-struct hodor_fri_proto {
-    int field_id = 0;
-    uint64_t n = 0;
-    uint32_t lde_factor = 0, out_coeffs = 0;
-    int steps = 0;
-    uint4* block = nullptr;      // one allocation for everything below
-    const uint4* lde = nullptr;  // layer-0 values (borrowed device pointer, or inside `owned_lde`)
-    uint4* owned_lde = nullptr;
-    std::vector<uint4*> nodes;   // nodes[0] = l0, nodes[i] = intermediate i-1
-    std::vector<uint4*> values;  // values[0] = lde, values[i] = intermediate i-1
-    uint4* roots = nullptr;      // steps + 1 digests
-    uint4* chal = nullptr;       // steps + 1 elements (the last one is never used by a fold)
-    uint4* final_coeffs = nullptr;  // ifft of the last layer (n >> steps elements)
-    uint4* path = nullptr;       // scratch for queries: 64 digests + 1 element
-};
-
-static void fri_destroy(hodor_fri_proto* p) {
+}  // extern "C"
+namespace hodor {
+void fri_destroy(hodor_fri_proto* p) {
     if (!p) return;
     Ctx* c = g_ctx;
     if (p->block) c ? c->pool_free(p->block) : (void)cudaFree(p->block);
     if (p->owned_lde) c ? c->pool_free(p->owned_lde) : (void)cudaFree(p->owned_lde);
     delete p;
 }
+}  // namespace hodor
+extern "C" {
 
 hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
                                        int lde_on_device, int field_id) {
     Ctx* c = ctx();
     if (!c) return nullptr;
     std::lock_guard<std::mutex> lk(c->mu);
+    return fri_commit_impl(c, lde, n, lde_factor, out_coeffs, lde_on_device, field_id);
+}
+}  // extern "C"
+
+namespace hodor {
+// the chain itself; caller holds Ctx::mu
+hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
+                                 int lde_on_device, int field_id) {
     const FieldOps* ops = field_ops(field_id);
     if (!ops) return nullptr;
     // the reference's asserts (src/fri/fri_on_values.rs:42-46) and its roots.pop() on an empty vec
@@ -1190,6 +1188,9 @@ hodor_fri_proto* hodor_cuda_fri_commit(const uint64_t* lde, uint64_t n, uint32_t
     if (rc) return nullptr;
     return p.release();
 }
+}  // namespace hodor
+
+extern "C" {
 
 void hodor_cuda_fri_free(hodor_fri_proto* p) {
     Ctx* c = g_ctx;

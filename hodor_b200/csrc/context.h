@@ -114,6 +114,8 @@ struct Ctx {
     // kernels whose dynamic shared memory attribute has been raised on this context's device
     std::set<const void*> configured_kernels;
     std::map<uint64_t, Fe> inv_cache;  // (field, log_n) -> omega_N^-1 of the FRI domain
+
+    struct Comm* comm = nullptr;  // multi-GPU state (sharded.cu); null until hodor_cuda_comm_init
     cudaEvent_t take_event();
 };
 
@@ -202,10 +204,52 @@ extern const FieldOps kOpsBlsFr, kOpsBn254Fr, kOpsStark252;
 const FieldOps* field_ops(int field_id);
 
 // field independent Merkle levels (merkle_common.cu)
-int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st);
+// leaf_log_g / leaf_chunk: leaves stored as 2^leaf_log_g cyclic-slice chunks (merkle.cuh LeafMap); 0 = natural order
+int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st,
+                  uint32_t leaf_log_g = 0, size_t leaf_chunk = 0);
 int merkle_path_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
                        cudaStream_t st);
 int merkle_paths_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, const uint64_t* d_indices,
                         uint32_t count, uint4* out, cudaStream_t st);
 
+
+int do_merkle(Ctx& c, const FieldOps* ops, const uint4* leaves, size_t n, uint4* nodes, uint4* root, uint4* chal,
+              cudaStream_t st, uint32_t leaf_log_g = 0, size_t leaf_chunk = 0);
+
 }  // namespace hodor
+
+// ---- FRI commit chain: the device-resident FRIProofPrototype (src/fri/mod.rs:107-117) ----------------
+struct hodor_fri_proto {
+    int field_id = 0;
+    uint64_t n = 0;
+    uint32_t lde_factor = 0, out_coeffs = 0;
+    int steps = 0;
+    uint4* block = nullptr;      // one allocation for everything below
+    const uint4* lde = nullptr;  // layer-0 values (borrowed device pointer, or inside `owned_lde`)
+    uint4* owned_lde = nullptr;
+    std::vector<uint4*> nodes;   // nodes[0] = l0, nodes[i] = intermediate i-1
+    std::vector<uint4*> values;  // values[0] = lde, values[i] = intermediate i-1
+    uint4* roots = nullptr;      // steps + 1 digests
+    uint4* chal = nullptr;       // steps + 1 elements (the last one is never used by a fold)
+    uint4* final_coeffs = nullptr;  // ifft of the last layer (n >> steps elements)
+    uint4* path = nullptr;       // scratch for queries: 64 digests + 1 element
+};
+
+
+namespace hodor {
+void fri_destroy(hodor_fri_proto* p);
+void comm_destroy(Ctx* c);  // sharded.cu
+// the whole chain on stream c->stream, synchronised on return; caller holds Ctx::mu
+hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
+                                 int lde_on_device, int field_id);
+}  // namespace hodor
+
+#define LOCKED_CTX()                          \
+    Ctx* c = ctx();                           \
+    if (!c) return HODOR_ERR_CUDA;            \
+    std::lock_guard<std::mutex> _lk(c->mu)
+#define GET_OPS(field_id)                         \
+    const FieldOps* ops = field_ops(field_id);    \
+    if (!ops) return HODOR_ERR_INVALID_ARG
+
+

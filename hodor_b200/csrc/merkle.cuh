@@ -223,18 +223,29 @@ DEV void st_digest(uint4* base, size_t idx, const Digest& d) {
     base[2 * idx + 1] = make_uint4(d.w[4], d.w[5], d.w[6], d.w[7]);
 }
 
+// Where leaf b of a tree lives.  Default: in[b].  Interleaved (a layer that arrived as G chunks of `chunk`
+// elements, chunk r holding the cyclic slice v[r + G*t] of the natural-order vector -- the receive side of
+// the all-to-all of the sharded FRI chain): in[(b mod G) * chunk + b / G], so the re-blocking costs index
+// arithmetic in this kernel's loads instead of a transposing copy through HBM.
+struct LeafMap {
+    uint32_t log_g;  // 0: identity
+    size_t chunk;
+};
+DEV size_t leaf_index(const LeafMap& m, size_t b) {
+    return m.log_g == 0 ? b : (b & (((size_t)1 << m.log_g) - 1)) * m.chunk + (b >> m.log_g);
+}
+
 // Thread-serial subtree over 2^K consecutive inputs starting at input index `first`.
 // Inputs are leaves (LEAF) or the digests of the level with `w_in` nodes.  The node covering
 // inputs [a*2^j, (a+1)*2^j) lives at heap index (w_in >> j) + a.
 template <int K, bool LEAF>
-DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, size_t w_in, size_t first) {
+DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, size_t w_in, size_t first, const LeafMap& lm) {
     if constexpr (K == 0) {
-        const Digest raw = ld_digest(in, first);
-        if constexpr (LEAF) return tree_hash_leaf(key, raw);
-        else return raw;
+        if constexpr (LEAF) return tree_hash_leaf(key, ld_digest(in, leaf_index(lm, first)));
+        else return ld_digest(in, first);
     } else {
-        const Digest l = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first);
-        const Digest r = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first + ((size_t)1 << (K - 1)));
+        const Digest l = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first, lm);
+        const Digest r = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first + ((size_t)1 << (K - 1)), lm);
         const Digest d = tree_hash_node(key, l, r);
         st_digest(nodes, (w_in >> K) + (first >> K), d);
         return d;
@@ -244,10 +255,10 @@ DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, si
 // grid-stride over groups of 2^K inputs; writes K node levels
 template <int K, bool LEAF>
 __global__ void __launch_bounds__(256) merkle_levels_kernel(const uint4* in, uint4* nodes, size_t w_in,
-                                                            const __grid_constant__ B2sState key) {
+                                                            const __grid_constant__ B2sState key, const LeafMap lm) {
     const size_t groups = w_in >> K;
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x)
-        merkle_subtree<K, LEAF>(key, in, nodes, w_in, g << K);
+        merkle_subtree<K, LEAF>(key, in, nodes, w_in, g << K, lm);
 }
 
 // Finishes a tree inside one block: from `w_in` inputs (leaves if LEAF, else the stored level of

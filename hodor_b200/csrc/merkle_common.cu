@@ -15,13 +15,13 @@ static unsigned grid_for(size_t work_items, unsigned block) {
 }
 
 template <int K, bool LEAF>
-static int launch_levels(Ctx& c, const uint4* in, uint4* nodes, size_t w_in, cudaStream_t st) {
+static int launch_levels(Ctx& c, const uint4* in, uint4* nodes, size_t w_in, cudaStream_t st, LeafMap lm = LeafMap{0, 0}) {
     // small levels: narrow blocks, so that a few thousand subtrees still spread over many SMs
     const size_t groups = w_in >> K;
     const unsigned block = groups >= 148 * 256 ? 256 : (groups >= 148 * 64 ? 128 : 32);
     {
         ProfScope ps(c, st, LEAF ? "merkle_levels_leaf" : "merkle_levels_node");
-        merkle_levels_kernel<K, LEAF><<<grid_for(groups, block), block, 0, st>>>(in, nodes, w_in, c.key);
+        merkle_levels_kernel<K, LEAF><<<grid_for(groups, block), block, 0, st>>>(in, nodes, w_in, c.key, lm);
     }
     HODOR_CUDA_TRY(cudaGetLastError());
     return HODOR_OK;
@@ -46,11 +46,15 @@ static size_t tail_max() {
 // Hashes the wide part of the tree.  On return *remaining_width is the width (<= tail_max()) of the
 // lowest level that has been written; 0 means nothing was done (n <= tail_max(), or too few leaves
 // for a subtree kernel: the tail kernel takes the leaves directly).
-int merkle_levels(Ctx& c, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st) {
+int merkle_levels(Ctx& c, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st,
+                  uint32_t leaf_log_g, size_t leaf_chunk) {
     *remaining_width = 0;
     const size_t tmax = tail_max();
-    if (n <= tmax || n < 16) return HODOR_OK;
-    int rc = launch_levels<3, true>(c, leaves, nodes, n, st);  // levels n/2, n/4, n/8
+    if (n <= tmax || n < 16) {
+        if (leaf_log_g) return fail(HODOR_ERR_INVALID_ARG, "internal: interleaved leaves need a tree wider than the tail kernel");
+        return HODOR_OK;
+    }
+    int rc = launch_levels<3, true>(c, leaves, nodes, n, st, LeafMap{leaf_log_g, leaf_chunk});  // levels n/2, n/4, n/8
     if (rc) return rc;
     size_t w = n >> 3;
     while (w > tmax) {

@@ -247,6 +247,41 @@ int hodor_cuda_ntt_shard_cols_dev(const void* d_in, void* d_out, uint32_t log_n,
 int hodor_cuda_ntt_shard_rows_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
                                   const uint64_t omega[4], int field_id, void* stream);
 
+/* Merkle tree over n leaves that arrived as G = 2^log_g chunks of n/G elements, chunk r holding the cyclic slice
+ * v[r + G*t] of the natural-order leaf vector (the receive side of the sharded chain's all-to-all): the
+ * re-blocking is index arithmetic inside the leaf kernel's loads, not a transposing copy.  n/G > 1024. */
+int hodor_cuda_merkle_build_shard_dev(const void* d_chunks, uint64_t n, uint32_t log_g, void* d_nodes, void* d_root,
+                                      void* d_challenge, int field_id, void* stream);
+
+/* ---- several GPUs: one process per GPU, NCCL for the exchange steps (multi-GPU) -------------
+ * The reference's only parallelism is threads on one host (src/fft/multicore.rs); these entry points are the
+ * `hodor_cuda_ntt_sharded` of SURVEY.md 8(b) and the north star's "2^24 -> 2^28 coset LDE plus full FRI commit
+ * chain on 8 x B200".  NCCL is loaded at run time (libnccl.so.2, or $HODOR_NCCL_LIB); nothing else needs it.
+ *
+ * Rendezvous: rank 0 calls hodor_cuda_comm_unique_id and ships the 128 bytes to the other ranks by whatever
+ * means the caller has (MPI, a file, torch.distributed); every rank then calls hodor_cuda_comm_init after
+ * hodor_cuda_init(device).  world must be a power of two <= 16; world == 1 needs no NCCL (id may be NULL). */
+int hodor_cuda_comm_unique_id(uint8_t id[128]);
+int hodor_cuda_comm_init(int rank, int world, const uint8_t id[128]);
+void hodor_cuda_comm_destroy(void);
+/* bytes_sent: payload this rank has pushed through NCCL since init.  Any pointer may be NULL. */
+int hodor_cuda_comm_info(int* rank, int* world, uint64_t* bytes_sent);
+/* Four-step (Bailey) NTT of length 2^log_n over the G ranks; best_fft's result (src/fft/fft.rs:5-125),
+ * distributed.  d_local: this rank's cyclic slice a[j*G + rank], n/G elements; d_out: n/G elements, the
+ * rank-th (n/G^2)-element chunk of every length-(n/G) block of the natural-order result:
+ * d_out[k2 * n/G^2 + k] = A[k2 * n/G + rank * n/G^2 + k].  Stream ordered; one all-to-all (each rank sends
+ * (G-1)/G of its slice once).  log_n >= 2 * log2(G). */
+int hodor_cuda_ntt_sharded(const void* d_local, void* d_out, uint32_t log_n, const uint64_t omega[4], int field_id,
+                           void* stream);
+/* ONE (coset) LDE 2^log_n -> 2^(log_n + log_factor) and its whole FRI commit chain
+ * (src/polynomials/mod.rs:544-609 then src/fri/fri_on_values.rs:11-159) over all ranks.  d_coeffs: 2^log_n
+ * coefficients, replicated on every rank.  Cosets are sharded with no communication, folds are local, each
+ * committed layer costs one all-to-all and a 32-byte all-gather.  Outputs in HOST memory, identical on every
+ * rank and bit-identical to the single-GPU chain: roots (steps + 1) * 32 B, challenges steps * 4 u64,
+ * final_coeffs out_coeffs * 4 u64 (any may be NULL).  Returns the number of folding steps.  G <= 2^log_factor. */
+int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint32_t out_coeffs,
+                               uint8_t* roots, uint64_t* challenges, uint64_t* final_coeffs, int field_id);
+
 /* Diagnostic: runs the fixed-operand multiplier behind every table multiply (Field::mul_pre)
  * against the Montgomery multiplier on the device, with its rare carry fix-up path forced on.
  * Returns the number of disagreeing threads (0 = pass). */

@@ -834,3 +834,64 @@ def test_pageable_host_memory_is_accepted(hodor, oracle):
     out = np.zeros(((1 << log_n) << log_f, 4), np.uint64)
     _ffi.check(_ffi.lib.hodor_cuda_lde(_p(a), log_n, log_f, 1, _p(out), fid))
     assert np.array_equal(out, oracle.lde(fid, a, log_n, 1 << log_f, True))
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-GPU entry points of the C ABI
+# ----------------------------------------------------------------------------------------------
+def test_merkle_build_shard_reindexes_cyclic_chunks(hodor, oracle):
+    """The leaf kernel of the sharded chain reads a layer that arrived as G cyclic-slice chunks; the tree must be
+    the tree of the natural-order vector (no transposing copy in between)."""
+    import torch
+    from hodor_b200 import _ffi
+    from hodor_b200 import device as dev
+    fid = 0
+    for log_g, log_n in ((1, 13), (2, 14), (3, 14), (4, 15)):
+        n, G = 1 << log_n, 1 << log_g
+        v = oracle.random_elements(fid, n, seed=40 + log_g)
+        chunks = np.concatenate([v[r::G] for r in range(G)])  # chunk r = v[r + G t]
+        d = dev.to_device(chunks)
+        nodes = dev.empty_elems(n)
+        root = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        chal = dev.empty_elems(1)
+        _ffi.check(_ffi.lib.hodor_cuda_merkle_build_shard_dev(d.data_ptr(), C.c_uint64(n), log_g, nodes.data_ptr(), root.data_ptr(),
+                                                              chal.data_ptr(), fid, torch.cuda.current_stream().cuda_stream))
+        want = oracle.merkle_create(fid, v)
+        assert np.array_equal(nodes.cpu().numpy().view(np.uint8).reshape(n, 32), want)
+        assert root.cpu().numpy().tobytes() == want[1].tobytes()
+    assert _ffi.lib.hodor_cuda_merkle_build_shard_dev(d.data_ptr(), C.c_uint64(2048), 2, nodes.data_ptr(), None, None, fid, None) \
+        == _ffi.ERR_INVALID_ARG
+
+
+def test_sharded_c_abi_world1(hodor, oracle):
+    """hodor_cuda_comm_init(0, 1) needs no NCCL; the sharded entry points then equal the single-GPU ones."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import sharded_check as sc
+    from hodor_b200 import multigpu as mg
+    assert mg.comm_init() == (0, 1)
+    for r in (sc.check_ntt(18, reps=1), sc.check_ntt(12, reps=1), sc.check_lde_fri(16, 3, reps=1), sc.check_lde_fri(12, 4, reps=1)):
+        assert r["ok"], r
+    roots, chals, fin = mg.lde_fri_sharded(__import__("hodor_b200").device.to_device(oracle.random_elements(0, 1 << 12, 5)), 12, 3, True, 2, 0)
+    want = oracle.fri_commit(0, oracle.lde(0, oracle.random_elements(0, 1 << 12, 5), 12, 8, True), 8, 2)
+    assert roots == want.roots() and np.array_equal(chals, want.challenges) and np.array_equal(fin, want.final_coefficients)
+    assert mg.bytes_sent() == 0
+
+
+def test_sharded_c_abi_two_gpus_under_torchrun():
+    """The NCCL composition itself: tools/sharded_check.py under torchrun on 2 GPUs compares the library's
+    four-step NTT and its sharded LDE + FRI chain with the single-GPU results.  Skipped on a one-GPU box."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tools", "sharded_check.py"), "18", "3", "20"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and len(lines) == 4 and all(l["ok"] for l in lines), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
