@@ -426,7 +426,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     h_in = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
     h_in.numpy().view(np.uint64)[:] = coeffs
     e2e_steps = max(2, args.steps)
-    CH = 4  # handles alive at once: 4 x (4 GiB values + 4 GiB nodes)
+    CH = 8  # handles alive at once: 8 x (4 GiB values + 4 GiB nodes)
     want_root = None
 
     def commit_chunk(src_ptr, count):
@@ -446,7 +446,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             done += m
         return r
 
-    want_root = e2e_commit(h_in.data_ptr(), CH)[0].tobytes()  # warm-up: pool blocks, tables
+    want_root = e2e_commit(h_in.data_ptr(), min(CH, e2e_steps))[0].tobytes()  # warm-up: pool blocks, tables
     barrier()
     l0 = dev.launch_count()
     t0 = time.perf_counter()
@@ -541,6 +541,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "matches_device_result": same}}
     del h_in
     os.sched_setaffinity(0, all_cpus)
+    _ffi.check(lib.hodor_cuda_trim())  # the committed-oracle blocks of this leg go back to the driver
 
     # ---- the paths with a real exchange step, through the C ABI (hodor_cuda_ntt_sharded / _lde_fri_sharded:
     # NCCL send/recv issued by the library), at EVERY N including 1, each checked against the single-GPU result
@@ -553,7 +554,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         idx = start + step * torch.arange(count, dtype=torch.int64, device="cuda")
         out = torch.empty((count, 4), dtype=torch.int64, device="cuda")
         for limb, mul in enumerate((0x2545F4914F6CDD1D, 0x5851F42D4C957F2D, 0x14057B7EF767814F, 0x27BB2EE687B0B0FD)):
-            x = (idx + (seed + 1) * 0x632BE59BD9B4E019) * mul
+            off = ((seed + 1) * 0x632BE59BD9B4E019) & (2**63 - 1)  # python int -> an int64 scalar
+            x = (idx + off) * mul
             x ^= (x >> 29)
             out[:, limb] = x * 0x369DEA0F31A53F85
         out[:, 3] &= 0x3FFFFFFFFFFFFFFF  # top limb < 2^62 < the modulus' top limb: canonical

@@ -56,6 +56,7 @@ _SIGS = {
     "hodor_cuda_last_error": (C.c_char_p, []),
     "hodor_cuda_last_error_code": (C.c_int, []),
     "hodor_cuda_workspace_bytes": (C.c_size_t, []),
+    "hodor_cuda_trim": (C.c_int, []),
     "hodor_cuda_launch_count": (C.c_uint64, []),
     "hodor_cuda_selftest_mul_pre": (C.c_int, [C.c_int]),
     "hodor_cuda_profile_begin": (C.c_int, []),

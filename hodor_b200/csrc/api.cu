@@ -119,10 +119,20 @@ void Ctx::pool_free(void* p) {
     }
     const size_t bytes = it->second;
     pool_live.erase(it);
+    if (bytes > pool_cache_cap) {
+        cudaFree(p);
+        return;
+    }
+    // keep the newest block; make room by releasing the oldest cached ones (a caller cycling through one shape
+    // reuses its block, whatever other shapes were cached before)
     size_t cached = 0;
     for (auto& b : pool_free_list) cached += b.second;
-    if (pool_free_list.size() >= 8 || cached + bytes > pool_cache_cap) cudaFree(p);
-    else pool_free_list.emplace_back(p, bytes);
+    while (!pool_free_list.empty() && (pool_free_list.size() >= 16 || cached + bytes > pool_cache_cap)) {
+        cached -= pool_free_list.front().second;
+        cudaFree(pool_free_list.front().first);
+        pool_free_list.erase(pool_free_list.begin());
+    }
+    pool_free_list.emplace_back(p, bytes);
 }
 
 cudaEvent_t Ctx::take_event() {
@@ -265,6 +275,7 @@ int hodor_cuda_init(int device) {
     HODOR_CUDA_TRY(cudaHostAlloc((void**)&c->pinned_small, Ctx::PINNED_SMALL_BYTES, cudaHostAllocDefault));
     c->key = b2s_keyed_state();
     if (const char* mb = getenv("HODOR_TABLE_BUDGET_MB")) c->full_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
+    if (const char* e = getenv("HODOR_FUSE_FOLD_COMMIT")) c->fuse_fold_commit = atoi(e) != 0;
     if (const char* mb = getenv("HODOR_POOL_CACHE_MB")) c->pool_cache_cap = (size_t)strtoull(mb, nullptr, 10) << 20;
     g_ctx = c.release();
     return HODOR_OK;
@@ -304,6 +315,15 @@ void hodor_cuda_shutdown(void) {
 
 const char* hodor_cuda_last_error(void) { return g_last_error.c_str(); }
 int hodor_cuda_last_error_code(void) { return g_last_code; }
+
+// Releases the cached (not live) pool blocks back to the driver.
+int hodor_cuda_trim(void) {
+    LOCKED_CTX();
+    HODOR_CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& b : c->pool_free_list) cudaFree(b.first);
+    c->pool_free_list.clear();
+    return HODOR_OK;
+}
 
 size_t hodor_cuda_workspace_bytes(void) {
     Ctx* c = g_ctx;
@@ -1179,6 +1199,15 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     const uint32_t log_n0 = log2u(n);
     for (int i = 0; i < steps && !rc; i++) {
         const size_t m = n >> i;
+        if (c->fuse_fold_commit && m / 2 > merkle_tail_width() && m / 2 >= 16) {
+            // fold + the bottom three levels of the new tree in one kernel, the rest of the tree as usual
+            rc = ops->fri_fold_commit(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], p->nodes[i + 1], st);
+            size_t w = 0;
+            if (!rc) rc = merkle_upper_levels(*c, p->nodes[i + 1], m / 16, &w, st);
+            if (!rc) rc = ops->merkle_tail(*c, p->nodes[i + 1], p->nodes[i + 1], (uint32_t)w, false, p->roots + 2 * (i + 1),
+                                           p->chal + 2 * (i + 1), st);
+            continue;
+        }
         rc = ops->fri_fold(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], 0, 1, st);
         if (rc) break;
         rc = do_merkle(*c, ops, p->values[i + 1], m / 2, p->nodes[i + 1], p->roots + 2 * (i + 1), p->chal + 2 * (i + 1), st);

@@ -92,7 +92,7 @@ struct Ctx {
     size_t full_budget = (size_t)24 << 30;  // HODOR_TABLE_BUDGET_MB overrides; 0 disables
 
     // freed prototype / tree / staging blocks kept for reuse (a committed 2^27 oracle is 8 GiB); HODOR_POOL_CACHE_MB
-    size_t pool_cache_cap = (size_t)40 << 30;
+    size_t pool_cache_cap = (size_t)64 << 30;
     std::vector<std::pair<void*, size_t>> pool_free_list;
     std::map<void*, size_t> pool_live;
     void* pool_alloc(size_t bytes);
@@ -114,6 +114,8 @@ struct Ctx {
     // kernels whose dynamic shared memory attribute has been raised on this context's device
     std::set<const void*> configured_kernels;
     std::map<uint64_t, Fe> inv_cache;  // (field, log_n) -> omega_N^-1 of the FRI domain
+
+    bool fuse_fold_commit = false;  // FRI chain: fold + bottom of the next tree in one kernel (HODOR_FUSE_FOLD_COMMIT=1; measured slower, profiles/r02_experiments.md)
 
     struct Comm* comm = nullptr;  // multi-GPU state (sharded.cu); null until hodor_cuda_comm_init
     cudaEvent_t take_event();
@@ -199,6 +201,10 @@ struct FieldOps {
                     uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st);
     int (*shard_rows)(Ctx&, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_g, uint32_t rank, const Fe& omega,
                       cudaStream_t st);
+    // one FRI layer fused with the bottom of its tree: folds `in` (n values) into `out` (n/2) and writes the node
+    // levels n/4, n/8, n/16 of `nodes` (heap of the n/2-leaf tree) from the values it holds in registers
+    int (*fri_fold_commit)(Ctx&, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
+                           uint4* nodes, cudaStream_t st);
 };
 extern const FieldOps kOpsBlsFr, kOpsBn254Fr, kOpsStark252;
 const FieldOps* field_ops(int field_id);
@@ -207,6 +213,8 @@ const FieldOps* field_ops(int field_id);
 // leaf_log_g / leaf_chunk: leaves stored as 2^leaf_log_g cyclic-slice chunks (merkle.cuh LeafMap); 0 = natural order
 int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st,
                   uint32_t leaf_log_g = 0, size_t leaf_chunk = 0);
+int merkle_upper_levels(Ctx&, uint4* nodes, size_t w, size_t* remaining_width, cudaStream_t st);
+size_t merkle_tail_width();
 int merkle_path_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
                        cudaStream_t st);
 int merkle_paths_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, const uint64_t* d_indices,

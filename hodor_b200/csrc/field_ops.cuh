@@ -644,9 +644,10 @@ struct Ops {
         return HODOR_OK;
     }
 
-    static int fri_fold(Ctx& c, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
-                        uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st) {
-        // omega_N^-1 of the INITIAL domain (src/fri/fri_on_values.rs:24-25), table over exponents < N/2
+    // omega_N^-e tables of the FRI domain N = 2^log_n0 (src/fri/fri_on_values.rs:24-40): the two-level table, and for
+    // the domains where the chain is long enough to pay for it the flat fixed-operand table of N/2 entries (32 * N
+    // bytes; cached and budgeted like the other expanded tables, two-level fallback otherwise)
+    static int fri_tables(Ctx& c, uint32_t log_n0, const PowTables** t, const uint4** flat, cudaStream_t st) {
         maybe_evict(c);
         auto& inv_cache = c.inv_cache;  // a host inversion is ~400 host multiplies
         Fe omega, omega_inv;
@@ -660,19 +661,24 @@ struct Ops {
         } else {
             omega_inv = cached->second;
         }
-        const PowTables* t = nullptr;
         std::vector<Fe> bases{omega_inv};
-        rc = get_pow_tables(c, &t, bases, log_n0 > 1 ? log_n0 - 1 : 1, nullptr, st);
+        rc = get_pow_tables(c, t, bases, log_n0 > 1 ? log_n0 - 1 : 1, nullptr, st);
+        if (rc) return rc;
+        *flat = nullptr;
+        if (log_n0 >= 16)
+            *flat = get_full_table(c, key_of("ffull", log_n0, 0, &omega_inv, 1), (*t)->two_level(), 0, 0, (size_t)1 << (log_n0 - 1),
+                                   1, -1, st);
+        return HODOR_OK;
+    }
+
+    static int fri_fold(Ctx& c, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
+                        uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st) {
+        const PowTables* t = nullptr;
+        const uint4* flat = nullptr;
+        int rc = fri_tables(c, log_n0, &t, &flat, st);
         if (rc) return rc;
         const size_t half = n / 2;
         const unsigned grid = (unsigned)((half + 255) / 256 > 148 * 16 ? 148 * 16 : (half + 255) / 256);
-        // flat fixed-operand table of omega_N^-e, e < N/2 (32 * N bytes; the device-side `omegas_inv`),
-        // for the domains where the chain is long enough to pay for it; cached and budgeted like the
-        // other expanded tables, two-level fallback otherwise
-        const uint4* flat = nullptr;
-        if (log_n0 >= 16)
-            flat = get_full_table(c, key_of("ffull", log_n0, 0, &omega_inv, 1), t->two_level(), 0, 0, (size_t)1 << (log_n0 - 1),
-                                  1, -1, st);
         {
             ProfScope ps(c, st, "fri_fold");
             if (flat)
@@ -681,6 +687,30 @@ struct Ops {
             else
                 fri_fold_kernel<F, false><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), nullptr, layer,
                                                                             chal, idx_offset, idx_stride, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
+    static int fri_fold_commit(Ctx& c, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
+                               uint4* nodes, cudaStream_t st) {
+        const PowTables* t = nullptr;
+        const uint4* flat = nullptr;
+        int rc = fri_tables(c, log_n0, &t, &flat, st);
+        if (rc) return rc;
+        const size_t half = n / 2, groups = half >> 3;
+        if (half < 16) return fail(HODOR_ERR_INVALID_ARG, "internal: fold_commit needs at least 16 outputs");
+        const unsigned block = groups >= 148 * 256 ? 256 : (groups >= 148 * 64 ? 128 : 32);
+        size_t g = (groups + block - 1) / block;
+        if (g > 148 * 16) g = 148 * 16;
+        {
+            ProfScope ps(c, st, "fri_fold_commit");
+            if (flat)
+                fri_fold_commit_kernel<F, true><<<(unsigned)g, block, 0, st>>>(in, out, nodes, half, t->two_level(), flat, layer, chal,
+                                                                               c.key, 0u);
+            else
+                fri_fold_commit_kernel<F, false><<<(unsigned)g, block, 0, st>>>(in, out, nodes, half, t->two_level(), nullptr, layer,
+                                                                                chal, c.key, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;
@@ -709,6 +739,7 @@ struct Ops {
         o.selftest_mul_pre = selftest_mul_pre;
         o.merkle_tail = merkle_tail;
         o.fri_fold = fri_fold;
+        o.fri_fold_commit = fri_fold_commit;
         o.shard_rows = shard_rows;
         return o;
     }

@@ -11,6 +11,7 @@
 // round trip.
 #pragma once
 #include "field.cuh"
+#include "merkle.cuh"
 #include "ntt.cuh"
 
 namespace hodor {
@@ -44,6 +45,48 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* o
             odd = fld.mul(odd, c);
         }
         st_fe(out, idx, fld.halve(fld.add(odd, even)));
+    }
+}
+
+// One layer fused with the bottom three levels of its Merkle tree (src/fri/fri_on_values.rs:61-119: fold, then
+// I::create(next_values)).  A thread owns 8 consecutive outputs: it folds them one by one, stores each value,
+// hashes it while it is still in registers and combines the hashes as a thread-serial 2^3 subtree, writing the
+// node levels half/2, half/4, half/8 of the new tree.  The layer's values are therefore read by no hashing
+// kernel (32 * half bytes of HBM reads and one launch per layer saved) and the fold's multiplier work (2
+// fixed-operand multiplies per leaf) issues between the ALU-bound compressions of other warps.
+#ifndef HODOR_FOLD_COMMIT_MINBLOCKS
+#define HODOR_FOLD_COMMIT_MINBLOCKS 1  // 3: cap the kernel at 85 registers (A/B build, profiles/r02_experiments.md)
+#endif
+template <class F, bool FLAT>
+__global__ void __launch_bounds__(256, HODOR_FOLD_COMMIT_MINBLOCKS) fri_fold_commit_kernel(const uint4* in, uint4* out, uint4* nodes, size_t half, TwoLevel winv,
+                                                              const uint4* winv_flat, uint32_t layer, const uint4* challenge,
+                                                              const __grid_constant__ B2sState key, uint32_t zero) {
+    const Field<F> fld(threadIdx.x & zero);
+    const Fe c = ld_fe(challenge, 0);
+    FePre cp;
+    if constexpr (FLAT) fld.make_pre(c, cp.w, cp.q);
+    const size_t groups = half >> 3;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+        auto leaf = [&](size_t idx) -> Digest {
+            const Fe f0 = ld_fe(in, idx), f1 = ld_fe(in, idx + half);
+            const Fe even = fld.add(f0, f1);
+            Fe odd = fld.sub(f0, f1);
+            const uint64_t e = (uint64_t)idx << layer;
+            if constexpr (FLAT) {
+                odd = mul_by(fld, odd, ld_pre(winv_flat, (size_t)e));
+                odd = mul_by(fld, odd, cp);
+            } else {
+                odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, e));
+                odd = fld.mul(odd, c);
+            }
+            const Fe v = fld.halve(fld.add(odd, even));
+            st_fe(out, idx, v);
+            Digest d;
+#pragma unroll
+            for (int i = 0; i < 8; i++) d.w[i] = v.v[i];
+            return tree_hash_leaf(key, d);
+        };
+        merkle_subtree_fn<3>(key, nodes, half, g << 3, leaf);
     }
 }
 

@@ -252,6 +252,21 @@ DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, si
     }
 }
 
+// The same subtree with the leaf hashes coming from a functor (leaf index -> hash of that leaf): lets a producer
+// kernel hash values it has just computed, while they are still in registers (fri.cuh: fold + commit).
+template <int K, class LeafHash>
+DEV Digest merkle_subtree_fn(const B2sState& key, uint4* nodes, size_t w_in, size_t first, LeafHash&& leaf_hash) {
+    if constexpr (K == 0) {
+        return leaf_hash(first);
+    } else {
+        const Digest l = merkle_subtree_fn<K - 1>(key, nodes, w_in, first, leaf_hash);
+        const Digest r = merkle_subtree_fn<K - 1>(key, nodes, w_in, first + ((size_t)1 << (K - 1)), leaf_hash);
+        const Digest d = tree_hash_node(key, l, r);
+        st_digest(nodes, (w_in >> K) + (first >> K), d);
+        return d;
+    }
+}
+
 // grid-stride over groups of 2^K inputs; writes K node levels
 template <int K, bool LEAF>
 __global__ void __launch_bounds__(256) merkle_levels_kernel(const uint4* in, uint4* nodes, size_t w_in,

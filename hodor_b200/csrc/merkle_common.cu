@@ -56,7 +56,14 @@ int merkle_levels(Ctx& c, const uint4* leaves, size_t n, uint4* nodes, size_t* r
     }
     int rc = launch_levels<3, true>(c, leaves, nodes, n, st, LeafMap{leaf_log_g, leaf_chunk});  // levels n/2, n/4, n/8
     if (rc) return rc;
-    size_t w = n >> 3;
+    return merkle_upper_levels(c, nodes, n >> 3, remaining_width, st);
+}
+
+// Continues a tree whose level of w nodes (heap [w, 2w)) is already written, down to the width the single-block
+// tail kernel takes over at.  Also the second half of the fused fold + leaf kernel's tree (fri.cuh).
+int merkle_upper_levels(Ctx& c, uint4* nodes, size_t w, size_t* remaining_width, cudaStream_t st) {
+    const size_t tmax = tail_max();
+    int rc = HODOR_OK;
     while (w > tmax) {
         int k = 0;
         while (k < 3 && (w >> (k + 1)) >= tmax) k++;  // land exactly on tmax or above
@@ -73,6 +80,8 @@ int merkle_levels(Ctx& c, const uint4* leaves, size_t n, uint4* nodes, size_t* r
     *remaining_width = w;
     return HODOR_OK;
 }
+
+size_t merkle_tail_width() { return tail_max(); }
 
 // out[0] = hash_leaf(values[index ^ 1]); out[1 + j] = sibling on the way up
 __global__ void merkle_path_kernel(const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
