@@ -252,6 +252,72 @@ def gpu_local_cpus(local_rank: int):
         return None
 
 
+def run_fib(args, dev, lib, _ffi, profile, cpu: bool, log_rows: int = 20, lde_factor: int = 16):
+    import torch
+    from hodor_b200 import fib_replay as R
+
+    t0 = time.perf_counter()
+    a, b = R.fibonacci_witness(FIELD, 1 << log_rows)
+    witness_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    prover = R.FibonacciProver(FIELD, log_rows, lde_factor, 1)
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    prover.prove(a, b)  # warm-up: tables, pool blocks
+    times = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr = prover.prove(a, b)
+        times.append((time.perf_counter() - t0) * 1e3)
+    l0 = dev.launch_count()
+    prof = profile(lambda: prover.prove(a, b))
+    launches = dev.launch_count() - l0
+    ksum = sum(r["total_ms"] for r in prof.values())
+    ok = all(hodor_verify(q, root) for q, root in zip(pr.f_queries + [pr.g_query], pr.f_iop_roots + [pr.g_iop_root]))
+    out = {"workload": f"Fibonacci AIR prove, trace 2^{log_rows} rows x 2 registers, blowup {lde_factor}, FRI to 1 coefficient: "
+                       "2 iNTT, 3 LDE 2^20 -> 2^24 + 3 trees, 7 coset NTT + 1 icoset NTT, DEEP (5 evaluate_at, 3 batch inversions "
+                       "over 2^24, elementwise passes), 2 FRI commit chains (21 trees each), queries",
+           "ms_per_proof": min(times), "ms_all": times, "setup_ms (Prover::new: ALI divisors on device)": setup_ms,
+           "witness_generation_s (host, not timed)": witness_s, "kernel_ms": ksum, "gpu_launches": launches,
+           "h2d_bytes_per_proof": int(a.nbytes + b.nbytes), "openings_verify": bool(ok),
+           "kernels": {k: {"launches": r["count"], "total_ms": round(r["total_ms"], 3)} for k, r in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])},
+           "timer": "host perf_counter around prove(): witness H2D, every kernel, transcript on the host, openings D2H",
+           "parity": "bit-exact against the big-int model of the same call sequence at 2^2 / 2^5 / 2^8 rows (tests/test_fib_prove.py)"}
+    if cpu:
+        # the same proof's hot-path components on the host cores (the reference's algorithms, oracle/): a LOWER bound
+        # of its prove() time -- the elementwise / DEEP passes and the AIR machinery are not included
+        from oracle import oracle as O
+        O.build()
+        cores = O.default_cpus()
+        n, N = 1 << log_rows, (1 << log_rows) * lde_factor
+        x = O.random_elements(FIELD, n, seed=5)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            O.ifft(FIELD, x, log_rows)
+        lde = None
+        for _ in range(3):
+            lde = O.lde(FIELD, x, log_rows, lde_factor, False, cpus=max(cores, lde_factor))
+            O.merkle_create(FIELD, lde, cpus=cores)
+        for _ in range(8):
+            O.fft(FIELD, x, log_rows, coset=True)
+        for _ in range(2):
+            O.fri_commit(FIELD, lde, lde_factor, 1, cpus=cores)
+        cpu_s = time.perf_counter() - t0
+        out["cpu_hot_path_components_s"] = cpu_s
+        out["cpu_cores"] = cores
+        out["cpu_note"] = ("2 iNTT + 3 x (LDE + Merkle tree) + 8 coset NTT + 2 FRI chains with the reference's CPU algorithms "
+                           "(oracle/hodor_oracle.c); a lower bound of the reference's prove(): DEEP / elementwise passes excluded")
+        out["speedup_vs_cpu_lower_bound"] = cpu_s * 1e3 / min(times)
+    del prover
+    _ffi.check(lib.hodor_cuda_trim())
+    return out
+
+
+def hodor_verify(query, root) -> bool:
+    import hodor_b200 as H
+    return bool(H.TrivialBlake2sIOP.verify_query(query, root))
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
@@ -575,6 +641,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             best = ms if best is None else min(best, ms)
         return best
 
+    def timed_local(fn, reps):
+        """This rank only: no collective inside (rank 0 times its single-GPU reference alone)."""
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     log_g = world.bit_length() - 1
     sharded = []
     sizes = [24, 26, 28] if not args.sweep else list(range(18, 29, 2))
@@ -595,7 +673,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             if rank == 0:
                 full = device_elements(nn, ln)
                 ref = dev.empty_elems(nn)
-                t1 = timed(lambda: dev.fft(full, ref, ln, False, FIELD), 3, 1) / 3
+                t1 = timed_local(lambda: dev.fft(full, ref, ln, False, FIELD), 3)
                 del full
                 chunk = m >> log_g
                 mine = ref.view(world, world, chunk, 4)[:, 0].reshape(m, 4)  # A[k2 * m + 0 * chunk + k]
@@ -699,6 +777,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 row["speedup_vs_cpu"] = row["cpu_ms"] / row["ms"]
                 row["cpu_cores"] = O.default_cpus()
 
+    # ---- configs[3]: Fibonacci AIR end-to-end prove, trace 2^20, blowup 16 (hot-path call sequence of
+    # src/prover/mod.rs:66-174 replayed on device-resident polynomials; hodor_b200/fib_replay.py)
+    fib = None
+    if world == 1 and not args.no_fib:
+        fib = run_fib(args, dev, lib, _ffi, profile, cpu=not args.no_cpu)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, dt = cpu_lde_sample(20, 2)
@@ -723,6 +807,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         line["sharded_lde_fri"] = sharded_fri
         if sweep is not None:
             line["ntt_sweep"] = sweep
+        if fib is not None:
+            line["fib_prove"] = fib
         emit(line)
 
 
@@ -735,6 +821,8 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="sharded legs: every even size 2^18..2^28 instead of 2^24/2^26/2^28")
     ap.add_argument("--no-sweep", action="store_true", help="skip the single-GPU NTT size sweep 2^18..2^28 (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fib", action="store_true", help="skip the Fibonacci prove leg (configs[3])")
+    ap.add_argument("--config", choices=["default", "fib"], default="default", help="fib: only the Fibonacci prove leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -751,6 +839,25 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+
+    if args.config == "fib":
+        if rank == 0:
+            import torch
+            import hodor_b200 as H
+            from hodor_b200 import _ffi
+            from hodor_b200 import device as dev
+            torch.cuda.set_device(local_rank)
+            H.init(local_rank)
+
+            def profile(fn):
+                _ffi.check(_ffi.lib.hodor_cuda_profile_begin())
+                fn()
+                buf = C.create_string_buffer(1 << 16)
+                _ffi.check(_ffi.lib.hodor_cuda_profile_end(buf, len(buf)))
+                return {r["name"]: r for r in json.loads(buf.value.decode())}
+
+            emit({"metric": "fib_prove_ms", "config": {"workload": "configs[3]"}, **run_fib(args, dev, _ffi.lib, _ffi, profile, not args.no_cpu)})
         return
 
     if world > 1:

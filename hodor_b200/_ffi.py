@@ -130,6 +130,7 @@ _SIGS = {
                                                 C.c_int, vp]),
     "hodor_cuda_lde_cosets_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                             C.c_int, vp]),
+    "hodor_cuda_distribute_powers_dev": (C.c_int, [vp, C.c_uint64, u64p, C.c_int, vp]),
     "hodor_cuda_elementwise_dev": (C.c_int, [C.c_int, vp, vp, vp, C.c_uint64, C.c_int, vp]),
     "hodor_cuda_poly_op_dev": (C.c_int, [C.c_int, vp, vp, u64p, C.c_uint64, vp, C.c_uint64, C.c_int, vp]),
     "hodor_cuda_batch_inversion_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 #include "context.h"
 
@@ -68,6 +69,53 @@ int Ctx::ws_release(cudaStream_t st) {
     HODOR_CUDA_TRY(cudaEventRecord(ws_event, st));
     ws_stream = st;
     ws_used = true;
+    return HODOR_OK;
+}
+
+// Host -> device copy of a caller buffer.  Pinned (cudaHostAlloc / cudaHostRegister) memory goes down as one
+// asynchronous copy.  Pageable memory -- what a Rust Vec<F> is -- would be staged by the driver through a single
+// thread at ~11 GB/s (measured: 47 ms for the 512 MiB of a 2^24 polynomial); here it is staged through two pinned
+// 32 MiB buffers filled by several host threads, so the copy runs at PCIe speed and overlaps the kernels already
+// enqueued.  Host-synchronous for pageable sources (the source may be reused on return either way only after the
+// caller's own stream synchronisation for pinned ones, as with cudaMemcpyAsync).
+int Ctx::h2d(void* dptr, const void* hptr, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return HODOR_OK;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, hptr) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pinned || bytes < ((size_t)8 << 20) || stage_threads <= 1) {
+        HODOR_CUDA_TRY(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, st));
+        return HODOR_OK;
+    }
+    constexpr size_t CHUNK = (size_t)32 << 20;
+    for (int b = 0; b < 2; b++) {
+        if (!stage[b]) {
+            HODOR_CUDA_TRY(cudaHostAlloc(&stage[b], CHUNK, cudaHostAllocDefault));
+            HODOR_CUDA_TRY(cudaEventCreateWithFlags(&stage_free[b], cudaEventDisableTiming));
+        }
+    }
+    size_t off = 0;
+    for (int k = 0; off < bytes; k++, off += CHUNK) {
+        const int b = k & 1;
+        const size_t len = bytes - off < CHUNK ? bytes - off : CHUNK;
+        if (stage_used[b]) HODOR_CUDA_TRY(cudaEventSynchronize(stage_free[b]));  // the last DMA out of this buffer (this call's or an earlier one's) has finished
+        const char* src = (const char*)hptr + off;
+        char* dst = (char*)stage[b];
+        const int T = stage_threads;
+        const size_t part = ((len + T - 1) / T + 4095) & ~(size_t)4095;
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) {
+            const size_t lo = (size_t)t * part;
+            if (lo >= len) break;
+            const size_t n = len - lo < part ? len - lo : part;
+            th.emplace_back([=] { memcpy(dst + lo, src + lo, n); });
+        }
+        memcpy(dst, src, len < part ? len : part);
+        for (auto& x : th) x.join();
+        HODOR_CUDA_TRY(cudaMemcpyAsync((char*)dptr + off, dst, len, cudaMemcpyHostToDevice, st));
+        HODOR_CUDA_TRY(cudaEventRecord(stage_free[b], st));
+        stage_used[b] = true;
+    }
     return HODOR_OK;
 }
 
@@ -275,6 +323,11 @@ int hodor_cuda_init(int device) {
     HODOR_CUDA_TRY(cudaHostAlloc((void**)&c->pinned_small, Ctx::PINNED_SMALL_BYTES, cudaHostAllocDefault));
     c->key = b2s_keyed_state();
     if (const char* mb = getenv("HODOR_TABLE_BUDGET_MB")) c->full_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
+    if (const char* e = getenv("HODOR_STAGE_THREADS")) c->stage_threads = atoi(e);
+    if (c->stage_threads == 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        c->stage_threads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+    }
     if (const char* e = getenv("HODOR_FUSE_FOLD_COMMIT")) c->fuse_fold_commit = atoi(e) != 0;
     if (const char* mb = getenv("HODOR_POOL_CACHE_MB")) c->pool_cache_cap = (size_t)strtoull(mb, nullptr, 10) << 20;
     g_ctx = c.release();
@@ -306,6 +359,10 @@ void hodor_cuda_shutdown(void) {
     if (g_ctx->ws_event) cudaEventDestroy(g_ctx->ws_event);
     cudaFree(g_ctx->small);
     if (g_ctx->pinned_small) cudaFreeHost(g_ctx->pinned_small);
+    for (int b = 0; b < 2; b++) {
+        if (g_ctx->stage[b]) cudaFreeHost(g_ctx->stage[b]);
+        if (g_ctx->stage_free[b]) cudaEventDestroy(g_ctx->stage_free[b]);
+    }
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_in);
     cudaStreamDestroy(g_ctx->copy_out);
@@ -577,6 +634,12 @@ int hodor_cuda_lde_cosets_dev(const void* d_coeffs, uint32_t log_n, uint32_t log
     return ops->ntt(*c, (const uint4*)d_coeffs, (uint4*)d_out, log_n, log_count, omega, &shift0, &step, 0, nullptr,
                     pick_stream(c, stream));
 }
+int hodor_cuda_distribute_powers_dev(void* d_a, uint64_t n, const uint64_t g[4], int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (n == 0) return HODOR_OK;
+    return ops->scale_pow(*c, (uint4*)d_a, (size_t)n, fe_from_u64(g), pick_stream(c, stream));
+}
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
                                void* stream) {
     LOCKED_CTX();
@@ -632,7 +695,7 @@ static int host_inplace(Ctx* c, uint64_t* a, size_t n, int (*body)(Ctx&, uint4*,
     int rc = c->ensure_io(0, n * 32);
     if (rc) return rc;
     uint4* d = (uint4*)c->io[0];
-    HODOR_CUDA_TRY(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    { int hrc = c->h2d(d, a, n * 32, c->stream); if (hrc) return hrc; }
     rc = body(*c, d, arg);
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(a, d, n * 32, cudaMemcpyDeviceToHost, c->stream));
@@ -689,7 +752,7 @@ int hodor_cuda_lde(const uint64_t* coeffs, uint32_t log_n, uint32_t log_factor, 
     if (rc) return rc;
     rc = c->ensure_io(1, total * 32);
     if (rc) return rc;
-    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], coeffs, n * 32, cudaMemcpyHostToDevice, c->stream));
+    { int hrc = c->h2d(c->io[0], coeffs, n * 32, c->stream); if (hrc) return hrc; }
     rc = do_lde(*c, ops, (const uint4*)c->io[0], (uint4*)c->io[1], log_n, log_factor, coset, c->stream);
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[1], total * 32, cudaMemcpyDeviceToHost, c->stream));
@@ -729,7 +792,7 @@ int hodor_cuda_lde_batch(const uint64_t* const* coeffs, uint64_t* const* outs, u
     auto step = [&](uint32_t i) -> int {
         const uint32_t b = i % nbuf;
         if (i >= nbuf) HODOR_CUDA_TRY(cudaStreamWaitEvent(c->copy_in, comp_done[b], 0));  // in_buf[b] consumed
-        HODOR_CUDA_TRY(cudaMemcpyAsync(in_buf[b], coeffs[i], n * 32, cudaMemcpyHostToDevice, c->copy_in));
+        { int hrc = c->h2d(in_buf[b], coeffs[i], n * 32, c->copy_in); if (hrc) return hrc; }
         HODOR_CUDA_TRY(cudaEventRecord(in_done[b], c->copy_in));
         HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, in_done[b], 0));
         if (i >= nbuf) HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, out_done[b], 0));  // out_buf[b] drained
@@ -841,7 +904,7 @@ int hodor_cuda_merkle_build(const uint64_t* leaves, uint64_t n, uint8_t* nodes, 
     if (rc) return rc;
     rc = c->ensure_io(1, n * 32);
     if (rc) return rc;
-    HODOR_CUDA_TRY(cudaMemcpyAsync(c->io[0], leaves, n * 32, cudaMemcpyHostToDevice, c->stream));
+    { int hrc = c->h2d(c->io[0], leaves, n * 32, c->stream); if (hrc) return hrc; }
     rc = do_merkle(*c, ops, (const uint4*)c->io[0], n, (uint4*)c->io[1], nullptr, nullptr, c->stream);
     if (rc) return rc;
     HODOR_CUDA_TRY(cudaMemcpyAsync(nodes, c->io[1], n * 32, cudaMemcpyDeviceToHost, c->stream));
@@ -908,8 +971,7 @@ hodor_tree* hodor_cuda_tree_commit(const uint64_t* values, uint64_t n, int value
     cudaStream_t st = c->stream;
     if (values_on_device) {
         t->values = (const uint4*)values;
-    } else if (cudaMemcpyAsync((void*)t->values, values, n * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-        cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(values)");
+    } else if (c->h2d((void*)t->values, values, n * 32, st)) {
         return nullptr;
     }
     int rc = do_merkle(*c, ops, t->values, n, t->nodes, t->root, t->chal, st);
@@ -959,7 +1021,7 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
         if (!coeffs_on_device) {
             const uint32_t b = i % nbuf;
             if (i >= nbuf) HODOR_CUDA_TRY(cudaStreamWaitEvent(c->copy_in, comp_done[b], 0));  // in_buf[b] consumed
-            HODOR_CUDA_TRY(cudaMemcpyAsync(in_buf[b], coeffs[i], n * 32, cudaMemcpyHostToDevice, c->copy_in));
+            { int hrc = c->h2d(in_buf[b], coeffs[i], n * 32, c->copy_in); if (hrc) return hrc; }
             HODOR_CUDA_TRY(cudaEventRecord(in_done[b], c->copy_in));
             HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, in_done[b], 0));
             src = (const uint4*)in_buf[b];
@@ -1165,10 +1227,7 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     } else {
         p->owned_lde = (uint4*)c->pool_alloc(n * 32);
         if (!p->owned_lde) return nullptr;
-        if (cudaMemcpyAsync(p->owned_lde, lde, n * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-            cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(lde)");
-            return nullptr;
-        }
+        if (c->h2d(p->owned_lde, lde, n * 32, st)) return nullptr;
         p->lde = p->owned_lde;
     }
     // layout (in 32-byte slots): l0 nodes n | per layer: nodes + values | roots | challenges | final | path scratch

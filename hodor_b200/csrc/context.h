@@ -101,6 +101,14 @@ struct Ctx {
     int ensure_workspace(size_t bytes);
     int ensure_io(int which, size_t bytes);
 
+    // host -> device copies of caller buffers: pageable sources are staged through pinned buffers by several
+    // host threads (HODOR_STAGE_THREADS, default min(8, cores / 2); 1 = leave it to the driver)
+    int h2d(void* dptr, const void* hptr, size_t bytes, cudaStream_t st);
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
+    bool stage_used[2] = {false, false};
+    int stage_threads = 0;
+
     // The workspace is shared by every multi-kernel entry point (multi-pass NTT / LDE, batch_inversion,
     // evaluate_at) and `_dev` calls may arrive on different caller streams: the host-side mutex orders the
     // enqueues, not the execution.  ws_acquire makes `st` wait for the last user of the workspace when that

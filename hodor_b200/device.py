@@ -170,6 +170,18 @@ class DevicePolynomial:
     def coset_lde(self, worker, factor: int) -> "DevicePolynomial":
         return self._lde(factor, True)
 
+    @staticmethod
+    def filled(field_id: int, size: int, value, form: str = "Values") -> "DevicePolynomial":
+        """A vector of `size` copies of one element (vec![value; size])."""
+        one = to_device(fld.limbs(value).reshape(1, 4))
+        return DevicePolynomial(field_id, one.expand(size, 4).contiguous(), form)
+
+    def distribute_powers(self, worker, g) -> None:
+        """:54-57 -> src/fft/mod.rs:110-123: a[j] <- a[j] * g^j."""
+        ensure_init()
+        check(lib.hodor_cuda_distribute_powers_dev(_ptr(self.coeffs), C.c_uint64(self.size()), _p(fld.limbs(g)), self.field_id,
+                                                   _stream()))
+
     # ---- elementwise ---------------------------------------------------------------------------
     def _op(self, op: int, other=None, scalar=None, exp: int = 0) -> None:
         ensure_init()

@@ -222,6 +222,8 @@ int hodor_cuda_merkle_top_dev(void* d_nodes, uint64_t w, void* d_root, void* d_c
 /* one FRI layer: d_out[idx], idx < n/2, from d_in (n values); challenge read from d_challenge */
 int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
                             const void* d_challenge, void* d_out, int field_id, void* stream);
+/* distribute_powers (src/fft/mod.rs:110-123) in place on a device vector: a[j] <- a[j] * g^j */
+int hodor_cuda_distribute_powers_dev(void* d_a, uint64_t n, const uint64_t g[4], int field_id, void* stream);
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
                                void* stream);
 int hodor_cuda_poly_op_dev(int op, const void* d_a, const void* d_b, const uint64_t scalar[4], uint64_t exp, void* d_out,
