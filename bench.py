@@ -700,6 +700,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         del local, out
         torch.cuda.empty_cache()
 
+    exchange_kind = ("single GPU: nothing exchanged" if world == 1 else
+                     (f"peer stores over NVLink ({mg.bytes_peer_stored()} B stored into peers' buffers by rank 0's kernels, "
+                      f"{mg.bytes_sent()} B through NCCL)" if mg.bytes_peer_stored() > 0 else
+                      f"NCCL send/recv all-to-all ({mg.bytes_sent()} B sent by rank 0)"))
+
     # ---- the north-star target: ONE 2^24 -> 2^28 coset LDE + full FRI commit chain over all ranks
     s_log_f = 4
     d_shared = device_elements(n, 4000)  # replicated coefficient vector
@@ -802,8 +807,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "ntt": ntt, "fri": fri,
         }
-        line["sharded_ntt"] = {"api": "hodor_cuda_ntt_sharded (C ABI; four-step, one NCCL all-to-all issued by the library)",
-                               "scaling": "strong", "sizes": sharded}
+        line["sharded_ntt"] = {"api": "hodor_cuda_ntt_sharded (C ABI; four-step; the exchange is fused into the last pass of the local "
+                                      "transform as NVLink peer stores, NCCL send/recv where peer mapping is unavailable)",
+                               "exchange": exchange_kind, "scaling": "strong", "sizes": sharded}
         line["sharded_lde_fri"] = sharded_fri
         if sweep is not None:
             line["ntt_sweep"] = sweep

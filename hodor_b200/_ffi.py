@@ -121,7 +121,7 @@ _SIGS = {
     "hodor_cuda_comm_unique_id": (C.c_int, [u8p]),
     "hodor_cuda_comm_init": (C.c_int, [C.c_int, C.c_int, u8p]),
     "hodor_cuda_comm_destroy": (None, []),
-    "hodor_cuda_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "hodor_cuda_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hodor_cuda_ntt_sharded": (C.c_int, [vp, vp, C.c_uint32, u64p, C.c_int, vp]),
     "hodor_cuda_lde_fri_sharded": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u8p, u64p, u64p, C.c_int]),
     "hodor_cuda_merkle_top_dev": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, vp]),

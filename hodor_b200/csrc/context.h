@@ -125,6 +125,13 @@ struct Ctx {
 
     bool fuse_fold_commit = false;  // FRI chain: fold + bottom of the next tree in one kernel (HODOR_FUSE_FOLD_COMMIT=1; measured slower, profiles/r02_experiments.md)
 
+    // step A of the sharded NTT: the last pass stores into the peers' receive buffers (ntt.cuh NttPass::peer)
+    struct PeerStore {
+        bool on = false;
+        uint32_t chunk_log = 0, rank = 0;
+        uint4* base[16] = {};
+    } peer_store;
+
     struct Comm* comm = nullptr;  // multi-GPU state (sharded.cu); null until hodor_cuda_comm_init
     cudaEvent_t take_event();
 };

@@ -462,6 +462,19 @@ struct Ops {
             p.coset_stride_hi = coset->stride_hi();
         }
         for (int k = 0; k < 7; k++) p.wr[k] = tw->wr[k];
+        // output scaling out_g^k (icoset_fft, step A of the sharded NTT) as one streamed fixed-operand multiply
+        // instead of two Montgomery multiplies, when the table fits the budget
+        if (out_pow && log_n >= 16) {
+            std::vector<Fe> kb{*out_g};
+            p.out_pow_full = get_full_table(c, key_of("ofull", log_n, (uint32_t)out_mode, kb.data(), 1), out_pow->two_level(), 0, 0, n, 1, -1, st);
+        }
+        if (c.peer_store.on) {  // set by hodor_cuda_ntt_sharded around step A (sharded.cu)
+            if (log_l != 0) return fail(HODOR_ERR_INVALID_ARG, "internal: peer stores with cosets");
+            p.peer_on = 1;
+            p.peer_chunk_log = c.peer_store.chunk_log;
+            p.peer_rank = c.peer_store.rank;
+            for (int k = 0; k < 16; k++) p.peer[k] = c.peer_store.base[k];
+        }
         // expanded tables for the transforms where they pay (>= 2^20): pass-1 inter-pass twiddles and
         // the per-coset scaling powers, one entry per element
         const uint4* tw_full = nullptr;

@@ -65,7 +65,13 @@ struct NttPass {
     const uint4* coset_full;
     TwoLevel coset;     // pass 1 of a scaled transform: shift_i^j tables, coset i at +i*coset_stride
     TwoLevel out_pow;   // PASS_OUT_POW
+    const uint4* out_pow_full;  // PASS_OUT_POW: out_pow^k as a flat fixed-operand table (FePre, n entries), or null
     FePre out_const;    // PASS_OUT_CONST
+    // Sharded four-step NTT, last pass of step A: instead of `out`, output k goes straight into the receive buffer
+    // of the rank that owns it for step B -- peer[k >> peer_chunk_log] + (peer_rank << peer_chunk_log) + (k & mask)
+    // -- through NVLink peer stores: the all-to-all happens inside this kernel, tile by tile, under its arithmetic.
+    uint4* peer[16];
+    uint32_t peer_on, peer_chunk_log, peer_rank;
     FePre wr[7];        // omega_16^k, k = 1..7  (omega_8 = wr[1], omega_4 = wr[3])
 };
 
@@ -359,8 +365,16 @@ __global__ void __launch_bounds__(PassOccupancy<B>::THREADS, PassOccupancy<B>::M
             if (p.mid1) midrev = (mid >> p.mid1) | ((mid & ((1u << p.mid1) - 1u)) << p.mid0);
             const size_t k = (size_t)k1 | ((size_t)midrev << p.b1) | ((size_t)kloc << (ln - B));
             if (p.flags & PASS_OUT_CONST) v = mul_by(fld, v, ld_param(p.out_const, oz));
-            if (p.flags & PASS_OUT_POW) v = fld.mul(v, two_level_pow(fld, p.out_pow, 0, 0, k));
-            st_fe(p.out, (size_t)i + (k << p.log_l), v);
+            if (p.flags & PASS_OUT_POW) {
+                if (p.out_pow_full != nullptr) v = mul_by(fld, v, ld_pre(p.out_pow_full, k));
+                else v = fld.mul(v, two_level_pow(fld, p.out_pow, 0, 0, k));
+            }
+            if (p.peer_on) {
+                const size_t mask = ((size_t)1 << p.peer_chunk_log) - 1;
+                st_fe(p.peer[k >> p.peer_chunk_log], ((size_t)p.peer_rank << p.peer_chunk_log) + (k & mask), v);
+            } else {
+                st_fe(p.out, (size_t)i + (k << p.log_l), v);
+            }
         }
     };
 
@@ -379,6 +393,9 @@ __global__ void __launch_bounds__(PassOccupancy<B>::THREADS, PassOccupancy<B>::M
         ntt_group<F, B, R3, R4, R1 + R2, false, false, false>(fld, p, sm, tid, oz, load_global, store_global);
         __syncthreads();
         ntt_group<F, B, R4, 0, R1 + R2 + R3, false, false, true>(fld, p, sm, tid, oz, load_global, store_global);
+    }
+    if constexpr (LAST) {
+        if (p.peer_on) __threadfence_system();  // peer stores are performed before the kernel counts as complete
     }
 }
 

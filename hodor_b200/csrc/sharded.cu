@@ -75,6 +75,12 @@ struct Comm {
     void* buf[2] = {nullptr, nullptr};  // grow-only exchange buffers of the sharded NTT
     size_t buf_bytes[2] = {0, 0};
     uint64_t bytes_sent = 0;            // payload this rank pushed through NCCL since init (bench evidence)
+    uint64_t bytes_peer_stored = 0;     // payload stored straight into peers' buffers by the fused last pass
+    // NVLink peer access to every rank's receive buffer buf[1] (CUDA IPC; one process per GPU)
+    void* peer_recv[16] = {};           // peer_recv[rank] == buf[1]
+    size_t peer_bytes = 0;              // size the mappings were made for (0: none)
+    int peer_state = 0;                 // 0 untried, 1 mapped, -1 unavailable (fall back to NCCL send/recv)
+    uint4* flag = nullptr;              // 64 B of device scratch for the barrier collectives
     int ensure(int which, size_t bytes) {
         if (bytes <= buf_bytes[which]) return HODOR_OK;
         if (buf[which]) {
@@ -89,9 +95,18 @@ struct Comm {
     }
 };
 
+static void close_peers(Comm& cm) {
+    for (int r = 0; r < cm.world; r++)
+        if (r != cm.rank && cm.peer_recv[r]) cudaIpcCloseMemHandle(cm.peer_recv[r]);
+    for (auto& p : cm.peer_recv) p = nullptr;
+    cm.peer_bytes = 0;
+}
+
 void comm_destroy(Ctx* c) {
     if (!c || !c->comm) return;
     cudaDeviceSynchronize();
+    close_peers(*c->comm);
+    if (c->comm->flag) cudaFree(c->comm->flag);
     if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
     for (int i = 0; i < 2; i++)
         if (c->comm->buf[i]) cudaFree(c->comm->buf[i]);
@@ -121,6 +136,82 @@ static int all_gather(Comm& cm, const void* send, void* recv, size_t bytes, cuda
     }
     HODOR_NCCL_TRY(g_nccl.AllGather(send, recv, bytes, ncclUint8, cm.comm, st));
     cm.bytes_sent += (uint64_t)(cm.world - 1) * bytes;
+    return HODOR_OK;
+}
+
+// A collective on 32 bytes: every rank has reached this point of its stream (and, stream ordered, finished
+// everything before it) when it completes.
+static int stream_barrier(Comm& cm, cudaStream_t st) {
+    if (cm.world == 1) return HODOR_OK;
+    if (!cm.flag) HODOR_CUDA_TRY(cudaMalloc((void**)&cm.flag, 32 * 17));
+    HODOR_NCCL_TRY(g_nccl.AllGather(cm.flag, cm.flag + 2, 32, ncclUint8, cm.comm, st));
+    return HODOR_OK;
+}
+
+// Maps every rank's receive buffer into this process (cudaIpc handles exchanged through NCCL).  Collective:
+// every rank calls it with the same `bytes` whenever its buffer was (re)allocated.  On any failure the
+// communicator falls back to NCCL send/recv for good (peer_state = -1) -- on every rank, by agreement.
+static int map_peers(Comm& cm, size_t bytes, cudaStream_t st) {
+    if (cm.peer_state == 1 && cm.peer_bytes == bytes) return HODOR_OK;
+    if (cm.peer_state == -1) return HODOR_OK;
+    close_peers(cm);
+    struct Msg {
+        cudaIpcMemHandle_t h;
+        int ok;
+        char pad[128 - sizeof(cudaIpcMemHandle_t) - sizeof(int)];
+    };
+    static_assert(sizeof(Msg) == 128, "one 128-byte record per rank");
+    Msg mine{};
+    mine.ok = (getenv("HODOR_NO_PEER_STORES") == nullptr) && cudaIpcGetMemHandle(&mine.h, cm.buf[1]) == cudaSuccess;
+    cudaGetLastError();
+    Msg* d = nullptr;
+    HODOR_CUDA_TRY(cudaMalloc((void**)&d, sizeof(Msg) * (size_t)(cm.world + 1)));
+    std::vector<Msg> all(cm.world);
+    int rc = HODOR_OK;
+    do {
+        if (cudaMemcpyAsync(d, &mine, sizeof(Msg), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = HODOR_ERR_CUDA; break; }
+        if (g_nccl.AllGather(d, d + 1, sizeof(Msg), ncclUint8, cm.comm, st) != ncclSuccess) { rc = HODOR_ERR_CUDA; break; }
+        if (cudaMemcpyAsync(all.data(), d + 1, sizeof(Msg) * cm.world, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = HODOR_ERR_CUDA; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = HODOR_ERR_CUDA; break; }
+    } while (0);
+    cudaFree(d);
+    if (rc) return fail(rc, "peer handle exchange failed");
+    bool ok = true;
+    for (int r = 0; r < cm.world; r++) ok = ok && all[r].ok;
+    int opened = 1;
+    if (ok) {
+        for (int r = 0; r < cm.world && opened; r++) {
+            if (r == cm.rank) {
+                cm.peer_recv[r] = cm.buf[1];
+            } else if (cudaIpcOpenMemHandle(&cm.peer_recv[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                cm.peer_recv[r] = nullptr;
+                opened = 0;
+            }
+        }
+    } else {
+        opened = 0;
+    }
+    // agree: peer stores only if EVERY rank mapped every buffer
+    int* d_ok = nullptr;
+    HODOR_CUDA_TRY(cudaMalloc((void**)&d_ok, sizeof(int) * 32 * (size_t)(cm.world + 1)));
+    std::vector<int> oks(32 * (size_t)cm.world);
+    int mine_ok[32] = {opened};
+    cudaMemcpyAsync(d_ok, mine_ok, sizeof(mine_ok), cudaMemcpyHostToDevice, st);
+    ncclResult_t nr = g_nccl.AllGather(d_ok, d_ok + 32, sizeof(mine_ok), ncclUint8, cm.comm, st);
+    cudaMemcpyAsync(oks.data(), d_ok + 32, sizeof(mine_ok) * cm.world, cudaMemcpyDeviceToHost, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(d_ok);
+    if (nr != ncclSuccess || ce != cudaSuccess) return fail(HODOR_ERR_CUDA, "peer agreement failed");
+    bool all_ok = true;
+    for (int r = 0; r < cm.world; r++) all_ok = all_ok && oks[32 * (size_t)r] == 1;
+    if (all_ok) {
+        cm.peer_state = 1;
+        cm.peer_bytes = bytes;
+    } else {
+        close_peers(cm);
+        cm.peer_state = -1;
+    }
     return HODOR_OK;
 }
 
@@ -192,12 +283,13 @@ void hodor_cuda_comm_destroy(void) {
     comm_destroy(c);
 }
 
-int hodor_cuda_comm_info(int* rank, int* world, uint64_t* bytes_sent) {
+int hodor_cuda_comm_info(int* rank, int* world, uint64_t* bytes_sent, uint64_t* bytes_peer_stored) {
     LOCKED_CTX();
     if (!c->comm) return fail(HODOR_ERR_INVALID_ARG, "hodor_cuda_comm_init() has not been called");
     if (rank) *rank = c->comm->rank;
     if (world) *world = c->comm->world;
     if (bytes_sent) *bytes_sent = c->comm->bytes_sent;
+    if (bytes_peer_stored) *bytes_peer_stored = c->comm->bytes_peer_stored;
     return HODOR_OK;
 }
 
@@ -222,13 +314,39 @@ int hodor_cuda_ntt_sharded(const void* d_local, void* d_out, uint32_t log_n, con
     ops->h_pow(w, (uint64_t)cm.rank, wg);
     if (cm.world == 1)  // nothing to exchange, and the G-point DFT is the identity
         return ops->ntt(*c, (const uint4*)d_local, (uint4*)d_out, log_n, 0, wm, nullptr, nullptr, 0, nullptr, st);
+    const size_t had = cm.buf_bytes[1];
     int rc = cm.ensure(0, m * 32);
     if (!rc) rc = cm.ensure(1, m * 32);
     if (rc) return rc;
-    rc = ops->ntt(*c, (const uint4*)d_local, (uint4*)cm.buf[0], log_n - cm.log_g, 0, wm, nullptr, nullptr, 3, &wg, st);
-    if (rc) return rc;
-    rc = all_to_all(cm, cm.buf[0], cm.buf[1], (m >> cm.log_g) * 32, st);
-    if (rc) return rc;
+    // multi-pass local transforms only: the single-block kernel (m <= 2^11) has no peer-store path
+    const bool want_peers = log_n - cm.log_g >= 12;
+    if (want_peers && (cm.peer_state == 0 || (cm.peer_state == 1 && cm.buf_bytes[1] != had))) {
+        rc = map_peers(cm, cm.buf_bytes[1], st);
+        if (rc) return rc;
+    }
+    if (want_peers && cm.peer_state == 1) {
+        // X fused into A: the last pass of the local transform stores every output into the receive buffer of the
+        // rank that needs it (NVLink peer stores, 256-byte runs), so the exchange overlaps the butterflies tile by
+        // tile.  Barrier 1: nobody is still reading its receive buffer from the previous call's step B (it ran
+        // before this point on every rank's stream).  Barrier 2: every peer's stores have landed.
+        rc = stream_barrier(cm, st);
+        if (rc) return rc;
+        c->peer_store.on = true;
+        c->peer_store.chunk_log = log_n - 2 * cm.log_g;
+        c->peer_store.rank = (uint32_t)cm.rank;
+        for (int r = 0; r < 16; r++) c->peer_store.base[r] = r < cm.world ? (uint4*)cm.peer_recv[r] : nullptr;
+        rc = ops->ntt(*c, (const uint4*)d_local, (uint4*)cm.buf[0], log_n - cm.log_g, 0, wm, nullptr, nullptr, 3, &wg, st);
+        c->peer_store.on = false;
+        if (rc) return rc;
+        cm.bytes_peer_stored += (uint64_t)(cm.world - 1) * (m >> cm.log_g) * 32;
+        rc = stream_barrier(cm, st);
+        if (rc) return rc;
+    } else {
+        rc = ops->ntt(*c, (const uint4*)d_local, (uint4*)cm.buf[0], log_n - cm.log_g, 0, wm, nullptr, nullptr, 3, &wg, st);
+        if (rc) return rc;
+        rc = all_to_all(cm, cm.buf[0], cm.buf[1], (m >> cm.log_g) * 32, st);
+        if (rc) return rc;
+    }
     return ops->shard_rows(*c, (const uint4*)cm.buf[1], (uint4*)d_out, log_n, cm.log_g, (uint32_t)cm.rank, w, st);
 }
 

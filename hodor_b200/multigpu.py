@@ -60,8 +60,16 @@ def comm_destroy() -> None:
 
 
 def bytes_sent() -> int:
+    """Payload this rank pushed through NCCL since comm_init."""
     n = C.c_uint64(0)
-    check(lib.hodor_cuda_comm_info(None, None, C.byref(n)))
+    check(lib.hodor_cuda_comm_info(None, None, C.byref(n), None))
+    return int(n.value)
+
+
+def bytes_peer_stored() -> int:
+    """Payload this rank's kernels stored straight into other ranks' buffers over NVLink since comm_init."""
+    n = C.c_uint64(0)
+    check(lib.hodor_cuda_comm_info(None, None, None, C.byref(n)))
     return int(n.value)
 
 

@@ -270,13 +270,17 @@ int hodor_cuda_merkle_build_shard_dev(const void* d_chunks, uint64_t n, uint32_t
 int hodor_cuda_comm_unique_id(uint8_t id[128]);
 int hodor_cuda_comm_init(int rank, int world, const uint8_t id[128]);
 void hodor_cuda_comm_destroy(void);
-/* bytes_sent: payload this rank has pushed through NCCL since init.  Any pointer may be NULL. */
-int hodor_cuda_comm_info(int* rank, int* world, uint64_t* bytes_sent);
+/* bytes_sent: payload this rank has pushed through NCCL since init; bytes_peer_stored: payload its kernels stored
+ * straight into other ranks' buffers over NVLink (the fused last pass of the sharded NTT).  Any pointer may be NULL. */
+int hodor_cuda_comm_info(int* rank, int* world, uint64_t* bytes_sent, uint64_t* bytes_peer_stored);
 /* Four-step (Bailey) NTT of length 2^log_n over the G ranks; best_fft's result (src/fft/fft.rs:5-125),
  * distributed.  d_local: this rank's cyclic slice a[j*G + rank], n/G elements; d_out: n/G elements, the
  * rank-th (n/G^2)-element chunk of every length-(n/G) block of the natural-order result:
- * d_out[k2 * n/G^2 + k] = A[k2 * n/G + rank * n/G^2 + k].  Stream ordered; one all-to-all (each rank sends
- * (G-1)/G of its slice once).  log_n >= 2 * log2(G). */
+ * d_out[k2 * n/G^2 + k] = A[k2 * n/G + rank * n/G^2 + k].  Stream ordered.  The one exchange (each rank ships
+ * (G-1)/G of its slice once) is fused into the last pass of the local transform: its stores go straight into
+ * the owning rank's receive buffer over NVLink (CUDA IPC peer mappings), bracketed by two 32-byte collectives;
+ * where peer mapping is unavailable ($HODOR_NO_PEER_STORES, or cudaIpc fails) it is an NCCL send/recv
+ * all-to-all between the two local steps.  log_n >= 2 * log2(G). */
 int hodor_cuda_ntt_sharded(const void* d_local, void* d_out, uint32_t log_n, const uint64_t omega[4], int field_id,
                            void* stream);
 /* ONE (coset) LDE 2^log_n -> 2^(log_n + log_factor) and its whole FRI commit chain
