@@ -110,6 +110,7 @@ _SIGS = {
     "hodor_cuda_fri_layer": (C.c_int, [vp, C.c_uint32, u8p, u64p]),
     "hodor_cuda_fri_layer_size": (C.c_uint64, [vp, C.c_uint32]),
     "hodor_cuda_fri_query": (C.c_int, [vp, C.c_uint32, C.c_uint64, u64p, u8p]),
+    "hodor_cuda_fri_produce_proof": (C.c_int, [vp, C.c_uint64, u64p, u64p, u8p]),
     "hodor_cuda_fri_commit_host": (C.c_int, [u64p, C.c_uint64, C.c_uint32, C.c_uint32, u8p, C.POINTER(u8p),
                                              C.POINTER(u64p), u64p, u8p, u64p, C.c_int]),
     "hodor_cuda_ntt_dev": (C.c_int, [vp, vp, C.c_uint32, u64p, C.c_int, vp]),

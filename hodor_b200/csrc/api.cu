@@ -1234,7 +1234,7 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     size_t slots = n;
     for (int i = 0; i < steps; i++) slots += 2 * (n >> (i + 1));
     const size_t last = n >> steps;
-    slots += 2 * (size_t)(steps + 1) + last + 80;
+    slots += 2 * (size_t)(steps + 1) + last + 80 + (size_t)(steps + 1) * 2 * 66 + 2 * (size_t)(steps + 2);
     p->block = (uint4*)c->pool_alloc(slots * 32);
     if (!p->block) return nullptr;
     uint4* cur = p->block;
@@ -1253,6 +1253,8 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     p->chal = take(steps + 1);
     p->final_coeffs = take(last);
     p->path = take(80);
+    p->proof_scratch = take((size_t)(steps + 1) * 2 * 66);
+    p->proof_idx = (uint64_t*)take(2 * (size_t)(steps + 2) / 4 + 1);
 
     int rc = do_merkle(*c, ops, p->lde, n, p->nodes[0], p->roots, p->chal, st);
     const uint32_t log_n0 = log2u(n);
@@ -1329,6 +1331,51 @@ int hodor_cuda_fri_query(const hodor_fri_proto* p, uint32_t layer, uint64_t natu
     if (value) HODOR_CUDA_TRY(cudaMemcpyAsync(value, p->values[layer] + 2 * natural_index, 32, cudaMemcpyDeviceToHost, st));
     HODOR_CUDA_TRY(cudaStreamSynchronize(st));
     return len;
+}
+// FRIProofPrototype::produce_proof (src/fri/query_producer.rs:10-53) in one call: for every committed layer the two
+// members of the coset of the running index (sorted, src/iop/trivial_coset_combiner.rs:31-43), their values and
+// authentication paths; then Domain::index_and_size_for_next_domain (src/domains/mod.rs:56-70).  One gather launch per
+// layer, one device-to-host copy and one synchronisation for the whole proof.
+//   indices: 2 * (steps + 1) u64;  values: 2 * (steps + 1) * 4 u64;
+//   paths:   for layer l (size n >> l) two paths of log2(n >> l) digests each, concatenated in layer order.
+// Returns the total number of path digests written.
+int hodor_cuda_fri_produce_proof(const hodor_fri_proto* p, uint64_t natural_first_element_index, uint64_t* indices, uint64_t* values,
+                                 uint8_t* paths) {
+    LOCKED_CTX();
+    if (!p) return fail(HODOR_ERR_INVALID_ARG, "null handle");
+    if (natural_first_element_index >= p->n) return fail(HODOR_ERR_INVALID_ARG, "query index out of range");
+    cudaStream_t st = c->stream;
+    const int layers = p->steps + 1;
+    std::vector<uint64_t> idx(2 * (size_t)layers);
+    uint64_t size = p->n, cur = natural_first_element_index;
+    for (int l = 0; l < layers; l++) {
+        const uint64_t pair = (cur + size / 2) % size;
+        idx[2 * l] = cur < pair ? cur : pair;
+        idx[2 * l + 1] = cur < pair ? pair : cur;
+        cur = cur < size / 2 ? cur : cur - size / 2;
+        size /= 2;
+    }
+    HODOR_CUDA_TRY(cudaMemcpyAsync(p->proof_idx, idx.data(), idx.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    for (int l = 0; l < layers; l++) {
+        int rc = merkle_paths_gather(*c, p->nodes[l], p->values[l], p->n >> l, p->proof_idx + 2 * l, 2,
+                                     p->proof_scratch + 2 * 66 * 2 * (size_t)l, st);
+        if (rc) return rc;
+    }
+    std::vector<uint8_t> host((size_t)layers * 2 * 66 * 32);
+    HODOR_CUDA_TRY(cudaMemcpyAsync(host.data(), p->proof_scratch, host.size(), cudaMemcpyDeviceToHost, st));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+    size_t out = 0;
+    for (int l = 0; l < layers; l++) {
+        const int len = (int)log2u(p->n >> l);
+        for (int q = 0; q < 2; q++) {
+            const uint8_t* slot = host.data() + ((size_t)l * 2 + q) * 66 * 32;
+            if (indices) indices[2 * l + q] = idx[2 * l + q];
+            if (values) memcpy(values + 4 * (2 * (size_t)l + q), slot + 64 * 32, 32);
+            if (paths) memcpy(paths + out * 32, slot, (size_t)len * 32);
+            out += (size_t)len;
+        }
+    }
+    return (int)out;
 }
 int hodor_cuda_fri_commit_host(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs, uint8_t* l0_nodes,
                                uint8_t** layer_nodes, uint64_t** layer_values, uint64_t* challenges, uint8_t* final_root,

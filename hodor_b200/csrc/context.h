@@ -256,6 +256,8 @@ struct hodor_fri_proto {
     uint4* chal = nullptr;       // steps + 1 elements (the last one is never used by a fold)
     uint4* final_coeffs = nullptr;  // ifft of the last layer (n >> steps elements)
     uint4* path = nullptr;       // scratch for queries: 64 digests + 1 element
+    uint4* proof_scratch = nullptr;  // produce_proof: 2 query slots (66 digests each) per layer
+    uint64_t* proof_idx = nullptr;   // produce_proof: 2 indices per layer
 };
 
 

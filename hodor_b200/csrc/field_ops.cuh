@@ -462,12 +462,6 @@ struct Ops {
             p.coset_stride_hi = coset->stride_hi();
         }
         for (int k = 0; k < 7; k++) p.wr[k] = tw->wr[k];
-        // output scaling out_g^k (icoset_fft, step A of the sharded NTT) as one streamed fixed-operand multiply
-        // instead of two Montgomery multiplies, when the table fits the budget
-        if (out_pow && log_n >= 16) {
-            std::vector<Fe> kb{*out_g};
-            p.out_pow_full = get_full_table(c, key_of("ofull", log_n, (uint32_t)out_mode, kb.data(), 1), out_pow->two_level(), 0, 0, n, 1, -1, st);
-        }
         if (c.peer_store.on) {  // set by hodor_cuda_ntt_sharded around step A (sharded.cu)
             if (log_l != 0) return fail(HODOR_ERR_INVALID_ARG, "internal: peer stores with cosets");
             p.peer_on = 1;
@@ -490,8 +484,14 @@ struct Ops {
                 if (step) kb.push_back(*step);
                 ckey = key_of("cfull", log_n, log_l, kb.data(), (int)kb.size());
             }
+            std::string okey;
+            if (out_pow) {
+                std::vector<Fe> kb{*out_g};
+                okey = key_of("ofull", log_n, (uint32_t)out_mode, kb.data(), 1);
+            }
             const size_t want = (c.full_tables.count(bkey) ? 0 : n * sizeof(FePre)) +
-                                (coset && !c.full_tables.count(ckey) ? n * L * sizeof(FePre) : 0);
+                                (coset && !c.full_tables.count(ckey) ? n * L * sizeof(FePre) : 0) +
+                                (out_pow && !c.full_tables.count(okey) ? n * sizeof(FePre) : 0);
             if (c.full_bytes + want > c.full_budget && !c.full_tables.empty()) {
                 cudaDeviceSynchronize();
                 for (auto& kv : c.full_tables) cudaFree(kv.second.first);
@@ -501,6 +501,10 @@ struct Ops {
             tw_full = get_full_table(c, bkey, tw->pw.two_level(), 0, 0, n, 1, (int)s0, st);
             if (coset)
                 coset_full = get_full_table(c, ckey, coset->two_level(), coset->stride_lo(), coset->stride_hi(), n, L, -1, st);
+            // output scaling out_g^k (icoset_fft, step A of the sharded NTT) as one streamed fixed-operand multiply
+            // instead of two Montgomery multiplies.  Fetched here, after the make-room step above: no pointer handed
+            // out by get_full_table may be fetched before it.
+            if (out_pow) p.out_pow_full = get_full_table(c, okey, out_pow->two_level(), 0, 0, n, 1, -1, st);
         }
         p.coset_full = coset_full;
         uint32_t below = log_n;

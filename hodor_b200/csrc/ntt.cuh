@@ -133,6 +133,11 @@ DEV FePre ld_param(const FePre& c, uint32_t opaque_zero) {
     return r;
 }
 
+#ifndef HODOR_PASS_PREFETCH
+#define HODOR_PASS_PREFETCH 0  // 1: L2 prefetch of every HBM operand at kernel start (A/B build, profiles/r02_experiments.md)
+#endif
+DEV void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 template <class F>
 DEV Fe two_level_pow(const Field<F>& fld, const TwoLevel& t, size_t lo_off, size_t hi_off, uint64_t e) {
     const Fe l = ld_fe(t.lo, lo_off + (e & ((1ull << t.lo_bits) - 1)));
@@ -379,6 +384,45 @@ __global__ void __launch_bounds__(PassOccupancy<B>::THREADS, PassOccupancy<B>::M
     };
 
     constexpr int R1 = G::R1, R2 = G::R2, R3 = G::R3, R4 = G::R4;
+#if HODOR_PASS_PREFETCH
+    // Every address this thread will touch in HBM is known now: ask L2 for its 8 inputs (and their coset-scaling
+    // entries) and for the 8 inter-pass twiddle entries it multiplies by at the very end, so that the demand loads
+    // of the rolled loops find them on chip (L2 hit ~250 cycles instead of ~700+ from DRAM).
+    {
+        constexpr int EPT = PassOccupancy<B>::EPT;
+        constexpr uint32_t T = (8u << B) / EPT;
+        if constexpr (!LAST) {
+            constexpr int SL1 = B - R1;
+#pragma unroll 1
+            for (int j = 0; j < (EPT >> R1); j++) {
+                const uint32_t q = tid + j * T, c = q & 7u, rest = q >> 3;
+                const uint32_t lo = rest & ((1u << SL1) - 1u), hi = rest >> SL1;
+                const uint32_t base = (hi << (SL1 + R1)) | lo;
+#pragma unroll
+                for (int d = 0; d < (1 << R1); d++) {
+                    const size_t idx = in_base + ((size_t)(base + ((uint32_t)d << SL1)) << p.s) + c;
+                    prefetch_l2(p.in + 2 * idx);
+                    if constexpr (SCALE_IN) {
+                        if (p.coset_full != nullptr) prefetch_l2(p.coset_full + 4 * ((size_t)coset_hi * n + idx));
+                    }
+                }
+            }
+            constexpr int RL = G::NGROUPS == 2 ? R2 : (G::NGROUPS == 3 ? R3 : R4);
+            if (p.tw_full != nullptr || p.tw_direct != nullptr) {
+#pragma unroll 1
+                for (int j = 0; j < (EPT >> RL); j++) {
+                    const uint32_t q = tid + j * T, c = q & 7u, base = (q >> 3) << RL;
+#pragma unroll
+                    for (int k = 0; k < (1 << RL); k++) {
+                        const uint32_t kloc = local_out_index<B>(base + k);
+                        if (p.tw_full != nullptr) prefetch_l2(p.tw_full + 4 * (((size_t)kloc << p.s) + col0 + c));
+                        else prefetch_l2(p.tw_direct + 4 * ((size_t)kloc * (col0 + c)));
+                    }
+                }
+            }
+        }
+    }
+#endif
     ntt_group<F, B, R1, B - R1, 0, true, SCALE_IN, false>(fld, p, sm, tid, oz, load_global, store_global);
     __syncthreads();
     if constexpr (G::NGROUPS == 2) {

@@ -111,15 +111,24 @@ class FRIProofPrototype:
 
     def produce_proof(self, iop_values: Optional[Polynomial], natural_first_element_index: int) -> FRIProof:
         """src/fri/query_producer.rs:10-53 (the leaf values are read from HBM, so `iop_values` is unused)."""
-        domain_size = self.initial_degree_plus_one * self.lde_factor
-        domain_idx = natural_first_element_index
-        queries, roots = [], []
-        for layer in range(self.num_steps + 1):
-            coset = TrivialCombiner.get_coset_for_natural_index(domain_idx, domain_size)
-            for idx in coset:
-                queries.append(self._query(layer, idx))
+        self._h()
+        layers = self.num_steps + 1
+        idx = np.zeros(2 * layers, np.uint64)
+        vals = np.zeros((2 * layers, 4), np.uint64)
+        depth0 = self._n.bit_length() - 1
+        total = sum(2 * (depth0 - l) for l in range(layers))
+        paths = np.zeros((total, 32), np.uint8)
+        got = check(lib.hodor_cuda_fri_produce_proof(self._handle, C.c_uint64(natural_first_element_index), _p(idx), _p(vals),
+                                                     paths.ctypes.data_as(u8p)))
+        assert got == total
+        queries, roots, off = [], [], 0
+        for layer in range(layers):
+            d = depth0 - layer
+            for q in range(2):
+                queries.append(TrivialBlake2sIopQuery(int(idx[2 * layer + q]), vals[2 * layer + q].copy(),
+                                                      [x.tobytes() for x in paths[off:off + d]]))
+                off += d
             roots.append(self._roots[layer])
-            domain_idx, domain_size = Domain.index_and_size_for_next_domain(domain_idx, domain_size)
         return FRIProof(queries, roots, self.final_coefficients.copy(), self.initial_degree_plus_one,
                         self.output_coeffs_at_degree_plus_one, self.lde_factor, self.field_id)
 

@@ -199,6 +199,12 @@ uint64_t hodor_cuda_fri_layer_size(const hodor_fri_proto* p, uint32_t layer);
  * value (4 u64) and path (log2(size) * 32 B, leaf-pair hash first).  Returns the path length. */
 int hodor_cuda_fri_query(const hodor_fri_proto* p, uint32_t layer, uint64_t natural_index, uint64_t value[4],
                          uint8_t* path);
+/* FRIProofPrototype::produce_proof / FriIop::prototype_into_proof (src/fri/query_producer.rs:10-53) in one call:
+ * for every committed layer the two members of the coset of the running index (sorted), their values and paths.
+ * indices: 2 * (steps + 1) u64; values: 2 * (steps + 1) * 4 u64; paths: for layer l (size n >> l) two paths of
+ * log2(n >> l) digests, concatenated in layer order (steps + 1 layers).  Returns the number of digests written. */
+int hodor_cuda_fri_produce_proof(const hodor_fri_proto* p, uint64_t natural_first_element_index, uint64_t* indices,
+                                 uint64_t* values, uint8_t* paths);
 /* Same as the reference signature: everything copied out to caller-allocated host buffers.
  * layer_nodes[i] / layer_values[i] hold (n >> (i+1)) entries.  Returns num_steps. */
 int hodor_cuda_fri_commit_host(const uint64_t* lde, uint64_t n, uint32_t lde_factor, uint32_t out_coeffs,
