@@ -394,11 +394,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (profiles/)
     traffic, pipes = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))[dom["name"]]
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[dom["name"]]
         traffic = cap["traffic"]
         pipes = {"fmaheavy_pipe_cycles_active_pct": cap["fmaheavy_pipe_cycles_active_pct"],
                  "alu_pipe_cycles_active_pct": cap["alu_pipe_cycles_active_pct"], "issue_active_pct": cap["issue_active_pct"],
-                 "source": "profiles/r01b_traffic.json (ncu --set full of the same kernel; tools/capture_profiles.sh)"}
+                 "source": "profiles/r02_traffic.json (ncu --set full of the same kernel; tools/capture_profiles.sh)"}
     except Exception:
         pass
     roofline = {
