@@ -655,7 +655,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     log_g = world.bit_length() - 1
     sharded = []
-    sizes = [24, 26, 28] if not args.sweep else list(range(18, 29, 2))
+    sizes = list(range(18, 29, 2)) if not args.sweep else list(range(18, 29))  # configs[4]: 2^18 .. 2^28
     for ln in sizes:
         nn = 1 << ln
         m = nn >> log_g
@@ -824,7 +824,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--sweep", action="store_true", help="sharded legs: every even size 2^18..2^28 instead of 2^24/2^26/2^28")
+    ap.add_argument("--sweep", action="store_true", help="sharded legs: every size 2^18..2^28 instead of the even ones")
     ap.add_argument("--no-sweep", action="store_true", help="skip the single-GPU NTT size sweep 2^18..2^28 (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fib", action="store_true", help="skip the Fibonacci prove leg (configs[3])")

@@ -373,6 +373,74 @@ class TrivialBlake2sIOP {  // :282-341
     Blake2sIopTree<F> tree;
 };
 
+// An oracle whose leaves and tree stay in HBM behind a `hodor_tree` handle: what Prover::prove keeps per register
+// between the commit phase and the query phase (src/prover/mod.rs:73-95, :142-151).  Same surface as
+// TrivialBlake2sIOP; `query` extracts value and path on the device.
+template <class F>
+class CommittedOracle {
+  public:
+    using Query = TrivialBlake2sIopQuery<F>;
+    // IOP::create on host values (copied in once)
+    static CommittedOracle create(const std::vector<F>& leafs) {
+        const size_t n = leafs.size();
+        if (n < 2 || (n & (n - 1))) throw std::logic_error("assert!(num_leafs == num_leafs.next_power_of_two())");
+        Digest root{};
+        hodor_tree* h = hodor_cuda_tree_commit(reinterpret_cast<const uint64_t*>(leafs.data()), n, 0, root.data(), F::ID);
+        if (!h) check(hodor_cuda_last_error_code() < 0 ? hodor_cuda_last_error_code() : HODOR_ERR_CUDA);
+        return CommittedOracle(h, root);
+    }
+    // `let lde = w.lde(&worker, factor)?; I::create(lde.as_ref())` for every polynomial, in one pipelined call
+    static std::vector<CommittedOracle> lde_commit_batch(const std::vector<Polynomial<F, Coefficients>>& polys, size_t factor,
+                                                         bool coset = false) {
+        std::vector<CommittedOracle> out;
+        if (polys.empty()) return out;
+        if (factor == 0 || (factor & (factor - 1))) throw std::logic_error("assert!(factor.is_power_of_two())");
+        uint32_t log_f = 0;
+        while (((size_t)1 << log_f) < factor) log_f++;
+        std::vector<const uint64_t*> in;
+        for (const auto& p : polys) {
+            if (p.size() != polys[0].size()) throw std::logic_error("lde_commit_batch: polynomials must have one size");
+            in.push_back(reinterpret_cast<const uint64_t*>(p.as_ref().data()));
+        }
+        std::vector<hodor_tree*> handles(polys.size(), nullptr);
+        std::vector<Digest> roots(polys.size());
+        check(hodor_cuda_lde_commit_batch(in.data(), (uint32_t)polys.size(), polys[0].exp, log_f, coset ? 1 : 0, 0, handles.data(),
+                                          reinterpret_cast<uint8_t*>(roots.data()), F::ID));
+        for (size_t i = 0; i < polys.size(); i++) out.push_back(CommittedOracle(handles[i], roots[i]));
+        return out;
+    }
+    uint64_t size() const { return hodor_cuda_tree_size(handle_.get()); }
+    Digest get_root() const { return root_; }
+    F get_challenge_scalar_from_root() const {
+        F c;
+        check(hodor_cuda_tree_root(handle_.get(), nullptr, c.l));
+        return c;
+    }
+    static bool verify_query(const Query& q, const Digest& root) {
+        return Blake2sIopTree<F>::verify(root, q.value(), q.path(), q.tree_index());
+    }
+    Query query(size_t natural_index) const {
+        size_t len = 0;
+        while (((uint64_t)1 << len) < size()) len++;
+        Query q;
+        q.index = natural_index;
+        q.path_.resize(len);
+        check(hodor_cuda_tree_query(handle_.get(), natural_index, q.value_.l, reinterpret_cast<uint8_t*>(q.path_.data())));
+        return q;
+    }
+    std::vector<F> values() const {  // the committed vector, copied back
+        std::vector<F> v(size());
+        check(hodor_cuda_tree_read(handle_.get(), 0, size(), reinterpret_cast<uint64_t*>(v.data()), nullptr));
+        return v;
+    }
+    const void* device_values() const { return hodor_cuda_tree_values(handle_.get()); }
+
+  private:
+    CommittedOracle(hodor_tree* h, const Digest& root) : handle_(h, &hodor_cuda_tree_free), root_(root) {}
+    std::shared_ptr<hodor_tree> handle_;
+    Digest root_;
+};
+
 // ---- FRI -------------------------------------------------------------------------------------
 template <class F>
 struct FRIProof {  // src/fri/mod.rs:140-154
@@ -428,14 +496,29 @@ class FRIProofPrototype {  // src/fri/mod.rs:107-138; trees and layer values sta
                                    reinterpret_cast<uint8_t*>(q.path_.data())));
         return q;
     }
-    FRIProof<F> produce_proof(size_t natural_first_element_index) const {  // src/fri/query_producer.rs:10-53
+    FRIProof<F> produce_proof(size_t natural_first_element_index) const {  // src/fri/query_producer.rs:10-53, one call
         FRIProof<F> proof;
-        size_t domain_size = initial_degree_plus_one * lde_factor, domain_idx = natural_first_element_index;
-        for (int layer = 0; layer <= steps_; layer++) {
-            for (size_t idx : Domain<F>::coset_for_natural_index_and_size(domain_idx, domain_size))
-                proof.queries.push_back(query(layer, idx));
-            proof.roots.push_back(roots_[layer]);
-            std::tie(domain_idx, domain_size) = Domain<F>::index_and_size_for_next_domain(domain_idx, domain_size);
+        const size_t layers = (size_t)steps_ + 1;
+        size_t depth0 = 0;
+        while (((size_t)1 << depth0) < n_) depth0++;
+        size_t total = 0;
+        for (size_t l = 0; l < layers; l++) total += 2 * (depth0 - l);
+        std::vector<uint64_t> idx(2 * layers);
+        std::vector<F> vals(2 * layers);
+        std::vector<Digest> paths(total);
+        check(hodor_cuda_fri_produce_proof(handle_.get(), natural_first_element_index, idx.data(), reinterpret_cast<uint64_t*>(vals.data()),
+                                           reinterpret_cast<uint8_t*>(paths.data())));
+        size_t off = 0;
+        for (size_t l = 0; l < layers; l++) {
+            for (int q = 0; q < 2; q++) {
+                TrivialBlake2sIopQuery<F> query;
+                query.index = idx[2 * l + q];
+                query.value_ = vals[2 * l + q];
+                query.path_.assign(paths.begin() + off, paths.begin() + off + (depth0 - l));
+                off += depth0 - l;
+                proof.queries.push_back(std::move(query));
+            }
+            proof.roots.push_back(roots_[l]);
         }
         proof.final_coefficients = final_coefficients;
         proof.initial_degree_plus_one = initial_degree_plus_one;
@@ -459,12 +542,7 @@ struct NaiveFriIop {  // src/fri/mod.rs:63-105
         hodor_fri_proto* h = hodor_cuda_fri_commit(reinterpret_cast<const uint64_t*>(lde_values.as_ref().data()),
                                                    lde_values.size(), (uint32_t)lde_factor,
                                                    (uint32_t)output_coeffs_at_degree_plus_one, 0, F::ID);
-        if (!h) {
-            const std::string msg = hodor_cuda_last_error();
-            if (msg.find("2-adicity") != std::string::npos) throw SynthesisError(msg);
-            if (msg.find("fri_commit:") != std::string::npos) throw std::logic_error(msg);
-            throw CudaError(msg);
-        }
+        if (!h) check(hodor_cuda_last_error_code() < 0 ? hodor_cuda_last_error_code() : HODOR_ERR_CUDA);  // DOMAIN -> SynthesisError, ...
         return FRIProofPrototype<F>(h, lde_values.size(), lde_factor, output_coeffs_at_degree_plus_one);
     }
     static FRIProof<F> prototype_into_proof(const FRIProofPrototype<F>& prototype, const Polynomial<F, Values>&,

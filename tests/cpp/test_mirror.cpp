@@ -232,6 +232,35 @@ static void test_one_fri_step() {
     CHECK(threw);
 }
 
+// the register loop of Prover::prove (src/prover/mod.rs:73-80, :142-151): lde + I::create with everything resident
+// in HBM, then openings from the handle; against the oracle's LDE and tree
+template <class F>
+static void test_committed_oracle() {
+    const uint32_t log_n = 10;
+    const size_t n = (size_t)1 << log_n, factor = 8;
+    std::vector<Polynomial<F, Coefficients>> polys;
+    for (int r = 0; r < 3; r++) polys.push_back(Polynomial<F, Coefficients>::from_coeffs(random_vec<F>(n, 700 + r)));
+    const auto oracles = CommittedOracle<F>::lde_commit_batch(polys, factor, false);
+    CHECK(oracles.size() == 3);
+    for (int r = 0; r < 3; r++) {
+        std::vector<F> want(n * factor);
+        oracle_lde(F::ID, reinterpret_cast<const uint64_t*>(polys[r].as_ref().data()), log_n, (uint32_t)factor, 0,
+                   reinterpret_cast<uint64_t*>(want.data()), 16);
+        std::vector<Digest> nodes(n * factor);
+        oracle_merkle_create(F::ID, reinterpret_cast<const uint64_t*>(want.data()), n * factor, reinterpret_cast<uint8_t*>(nodes.data()), 4);
+        CHECK(oracles[r].size() == n * factor);
+        CHECK(oracles[r].get_root() == nodes[1]);
+        CHECK(oracles[r].values() == want);
+        CHECK(oracles[r].get_challenge_scalar_from_root() == Blake2sIopTree<F>::encode_root_into_challenge(nodes[1]));
+        for (size_t idx : {(size_t)0, (size_t)1, n * factor / 2 + 5, n * factor - 1}) {
+            const auto q = oracles[r].query(idx);
+            CHECK(q.value() == want[idx]);
+            CHECK(CommittedOracle<F>::verify_query(q, oracles[r].get_root()));
+        }
+        CHECK(CommittedOracle<F>::create(want).get_root() == nodes[1]);
+    }
+}
+
 template <class F>
 static void test_domain() {
     CHECK(Domain<F>::new_for_size(5).size == 8);
@@ -255,6 +284,7 @@ static void run_all(const char* name) {
     test_batch_inversion_and_evaluate<F>();
     test_small_iop<F>();
     test_one_fri_step<F>();
+    test_committed_oracle<F>();
     std::printf("%s: %s\n", name, failures == before ? "ok" : "FAILED");
 }
 
