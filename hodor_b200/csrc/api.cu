@@ -600,7 +600,7 @@ int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domai
     if (!is_pow2(n) || n < 2 || !is_pow2(initial_domain_size) || (initial_domain_size >> layer) != n)
         return fail(HODOR_ERR_INVALID_ARG, "fri_fold: n must equal initial_domain_size >> layer, both powers of two");
     return ops->fri_fold(*c, (const uint4*)d_in, n, log2u(initial_domain_size), layer, (const uint4*)d_challenge,
-                         (uint4*)d_out, 0, 1, pick_stream(c, stream));
+                         (uint4*)d_out, 0, 1, 0, pick_stream(c, stream));
 }
 int hodor_cuda_fri_fold_shard_dev(const void* d_in, uint64_t n_local, uint64_t initial_domain_size, uint32_t layer,
                                   uint32_t log_g, uint32_t rank, const void* d_challenge, void* d_out, int field_id,
@@ -612,7 +612,7 @@ int hodor_cuda_fri_fold_shard_dev(const void* d_in, uint64_t n_local, uint64_t i
         ((initial_domain_size >> layer) >> log_g) != n_local)
         return fail(HODOR_ERR_INVALID_ARG, "fri_fold_shard: n_local must equal (initial_domain_size >> layer) / G, >= 2");
     return ops->fri_fold(*c, (const uint4*)d_in, n_local, log2u(initial_domain_size), layer, (const uint4*)d_challenge,
-                         (uint4*)d_out, rank, g, pick_stream(c, stream));
+                         (uint4*)d_out, rank, g, 0, pick_stream(c, stream));
 }
 int hodor_cuda_lde_cosets_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint32_t first_coset,
                               uint32_t coset_stride, uint32_t log_count, void* d_out, int field_id, void* stream) {
@@ -1269,7 +1269,7 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
                                            p->chal + 2 * (i + 1), st);
             continue;
         }
-        rc = ops->fri_fold(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], 0, 1, st);
+        rc = ops->fri_fold(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], 0, 1, 0, st);
         if (rc) break;
         rc = do_merkle(*c, ops, p->values[i + 1], m / 2, p->nodes[i + 1], p->roots + 2 * (i + 1), p->chal + 2 * (i + 1), st);
     }

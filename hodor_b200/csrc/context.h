@@ -213,7 +213,7 @@ struct FieldOps {
     int (*merkle_tail)(Ctx&, const uint4* in, uint4* nodes, uint32_t w_in, bool leaf, uint4* root, uint4* chal,
                        cudaStream_t st);
     int (*fri_fold)(Ctx&, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
-                    uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st);
+                    uint64_t idx_offset, uint64_t idx_stride, uint32_t blk_log, cudaStream_t st);
     int (*shard_rows)(Ctx&, const uint4* in, uint4* out, uint32_t log_n, uint32_t log_g, uint32_t rank, const Fe& omega,
                       cudaStream_t st);
     // one FRI layer fused with the bottom of its tree: folds `in` (n values) into `out` (n/2) and writes the node
@@ -229,6 +229,12 @@ const FieldOps* field_ops(int field_id);
 int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st,
                   uint32_t leaf_log_g = 0, size_t leaf_chunk = 0);
 int merkle_upper_levels(Ctx&, uint4* nodes, size_t w, size_t* remaining_width, cudaStream_t st);
+// bottom k (1..3) levels only: leaves -> the level of n >> k nodes, written at heap[(n >> k), 2 (n >> k))
+int merkle_leaf_blocks(Ctx&, const uint4* leaves, size_t n, int k, uint4* heap, cudaStream_t st);
+// the tree above a level of w digests given in `level` (natural order, or 2^log_g cyclic chunks of `chunk` digests):
+// writes heap [.., w) down to the tail width; *remaining_width as merkle_levels
+int merkle_from_level(Ctx&, const uint4* level, size_t w, uint4* nodes, size_t* remaining_width, cudaStream_t st,
+                      uint32_t log_g, size_t chunk);
 size_t merkle_tail_width();
 int merkle_path_gather(Ctx&, const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
                        cudaStream_t st);

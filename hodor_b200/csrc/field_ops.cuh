@@ -689,7 +689,7 @@ struct Ops {
     }
 
     static int fri_fold(Ctx& c, const uint4* in, size_t n, uint32_t log_n0, uint32_t layer, const uint4* chal, uint4* out,
-                        uint64_t idx_offset, uint64_t idx_stride, cudaStream_t st) {
+                        uint64_t idx_offset, uint64_t idx_stride, uint32_t blk_log, cudaStream_t st) {
         const PowTables* t = nullptr;
         const uint4* flat = nullptr;
         int rc = fri_tables(c, log_n0, &t, &flat, st);
@@ -700,10 +700,10 @@ struct Ops {
             ProfScope ps(c, st, "fri_fold");
             if (flat)
                 fri_fold_kernel<F, true><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), flat, layer, chal,
-                                                                           idx_offset, idx_stride, 0u);
+                                                                           idx_offset, idx_stride, blk_log, 0u);
             else
                 fri_fold_kernel<F, false><<<grid ? grid : 1, 256, 0, st>>>(in, out, half, t->two_level(), nullptr, layer,
-                                                                            chal, idx_offset, idx_stride, 0u);
+                                                                            chal, idx_offset, idx_stride, blk_log, 0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;

@@ -16,7 +16,9 @@
 
 namespace hodor {
 
-// `in` holds the slice v[idx_offset + idx_stride * t] of the layer (offset 0, stride 1: the whole
+// `in` holds, at local position t, element  idx(t) = ((t >> blk_log) * idx_stride << blk_log) + idx_offset + (t & (2^blk_log - 1))
+// of the layer: blocks of 2^blk_log adjacent elements dealt round-robin (blk_log 0: v[idx_offset + idx_stride * t]).
+// (offset 0, stride 1: the whole
 // layer; offset r, stride G: rank r's cyclic slice of a layer sharded over G GPUs, whose fold pairs
 // (t, t + half) are then both local).
 // FLAT: the twiddle omega_N^-e is one 64-byte fixed-operand entry of a flat N/2-entry table (the
@@ -26,7 +28,7 @@ namespace hodor {
 template <class F, bool FLAT>
 __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* out, size_t half, TwoLevel winv,
                                                        const uint4* winv_flat, uint32_t layer, const uint4* challenge,
-                                                       uint64_t idx_offset, uint64_t idx_stride, uint32_t zero) {
+                                                       uint64_t idx_offset, uint64_t idx_stride, uint32_t blk_log, uint32_t zero) {
     const Field<F> fld(threadIdx.x & zero);
     const Fe c = ld_fe(challenge, 0);
     FePre cp;
@@ -36,7 +38,8 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* o
         const Fe f0 = ld_fe(in, idx), f1 = ld_fe(in, idx + half);
         const Fe even = fld.add(f0, f1);
         Fe odd = fld.sub(f0, f1);
-        const uint64_t e = (idx_offset + idx_stride * (uint64_t)t) << layer;
+        const uint64_t e = ((((uint64_t)t >> blk_log) * idx_stride << blk_log) + idx_offset + ((uint64_t)t & (((uint64_t)1 << blk_log) - 1)))
+                           << layer;
         if constexpr (FLAT) {
             odd = mul_by(fld, odd, ld_pre(winv_flat, (size_t)e));
             odd = mul_by(fld, odd, cp);

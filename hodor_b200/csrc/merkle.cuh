@@ -242,7 +242,7 @@ template <int K, bool LEAF>
 DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, size_t w_in, size_t first, const LeafMap& lm) {
     if constexpr (K == 0) {
         if constexpr (LEAF) return tree_hash_leaf(key, ld_digest(in, leaf_index(lm, first)));
-        else return ld_digest(in, first);
+        else return ld_digest(in, leaf_index(lm, first));  // a node level may arrive as cyclic chunks as well
     } else {
         const Digest l = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first, lm);
         const Digest r = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first + ((size_t)1 << (K - 1)), lm);

@@ -83,6 +83,34 @@ int merkle_upper_levels(Ctx& c, uint4* nodes, size_t w, size_t* remaining_width,
 
 size_t merkle_tail_width() { return tail_max(); }
 
+int merkle_leaf_blocks(Ctx& c, const uint4* leaves, size_t n, int k, uint4* heap, cudaStream_t st) {
+    if ((n >> k) == 0) return fail(HODOR_ERR_INVALID_ARG, "internal: leaf blocks larger than the vector");
+    switch (k) {
+        case 1: return launch_levels<1, true>(c, leaves, heap, n, st);
+        case 2: return launch_levels<2, true>(c, leaves, heap, n, st);
+        case 3: return launch_levels<3, true>(c, leaves, heap, n, st);
+    }
+    return fail(HODOR_ERR_INVALID_ARG, "internal: leaf block size must be 2, 4 or 8");
+}
+
+int merkle_from_level(Ctx& c, const uint4* level, size_t w, uint4* nodes, size_t* remaining_width, cudaStream_t st,
+                      uint32_t log_g, size_t chunk) {
+    const size_t tmax = tail_max();
+    if (w <= tmax || w < 4) return fail(HODOR_ERR_INVALID_ARG, "internal: level too narrow for the level kernels");
+    int k = 0;
+    while (k < 3 && (w >> (k + 1)) >= tmax) k++;
+    if (k == 0) k = 1;
+    const LeafMap lm{log_g, chunk};
+    int rc;
+    switch (k) {
+        case 1: rc = launch_levels<1, false>(c, level, nodes, w, st, lm); break;
+        case 2: rc = launch_levels<2, false>(c, level, nodes, w, st, lm); break;
+        default: rc = launch_levels<3, false>(c, level, nodes, w, st, lm); break;
+    }
+    if (rc) return rc;
+    return merkle_upper_levels(c, nodes, w >> k, remaining_width, st);
+}
+
 // out[0] = hash_leaf(values[index ^ 1]); out[1 + j] = sibling on the way up
 __global__ void merkle_path_kernel(const uint4* nodes, const uint4* values, size_t size, size_t index, uint4* out,
                                    const __grid_constant__ B2sState key) {

@@ -215,11 +215,14 @@ static int map_peers(Comm& cm, size_t bytes, cudaStream_t st) {
     return HODOR_OK;
 }
 
-// parts[r][t] = v[r + G*t]  ->  out[r + G*t]   (the tail of the sharded chain: a few thousand elements)
-__global__ void interleave_kernel(const uint4* parts, uint4* out, size_t per_rank, uint32_t log_g) {
+// parts[r][t] = the t-th local element of rank r, blocks of 2^blk_log adjacent elements dealt round-robin:
+// natural index i = ((t >> blk_log) * G + r) << blk_log | (t & (B - 1)).  Gathers natural order (the tail of the
+// sharded chain: a few tens of thousands of elements).
+__global__ void interleave_kernel(const uint4* parts, uint4* out, size_t per_rank, uint32_t log_g, uint32_t blk_log) {
     const size_t total = per_rank << log_g;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i & (((size_t)1 << log_g) - 1), t = i >> log_g;
+        const size_t c = i & (((size_t)1 << blk_log) - 1), blk = i >> blk_log;
+        const size_t r = blk & (((size_t)1 << log_g) - 1), t = ((blk >> log_g) << blk_log) | c;
         out[2 * i] = parts[2 * (r * per_rank + t)];
         out[2 * i + 1] = parts[2 * (r * per_rank + t) + 1];
     }
@@ -351,13 +354,16 @@ int hodor_cuda_ntt_sharded(const void* d_local, void* d_out, uint32_t log_n, con
 }
 
 // ONE coset LDE 2^log_n -> 2^(log_n + log_factor) plus its FRI commit chain over all ranks (the north star).
-// d_coeffs (2^log_n elements) is replicated on every rank.  Rank r computes the cosets i == r (mod G) with no
-// communication: its cyclic slice v[r + G t] of the natural-order LDE.  FRI fold pairs (idx, idx + M/2) have
-// equal residues mod G, so every fold is local.  A committed layer costs one all-to-all (cyclic slice ->
-// natural-order block, re-indexed inside the leaf kernel's loads), a local subtree whose root is node G + r of
-// the reference's heap, an all-gather of the G sub-roots (32 B each) and the top log2 G levels + root ->
-// challenge redundantly on every GPU; the challenge stays in HBM for the next fold.  Below 2^16 values the
-// strictly serial rest of the chain is finished by every rank with the single-GPU chain.
+// d_coeffs (2^log_n elements) is replicated on every rank.  Rank r computes the B = L/G cosets r*B .. r*B + B - 1
+// (capped at 8; cosets are independent) with no communication: blocks of B adjacent elements of the natural-order
+// LDE dealt round-robin, v[(k*G + r)*B + c].  FRI fold pairs (idx, idx + M/2) stay on one rank (M/2 is a multiple
+// of B*G), so every fold is local and the next layer has the same distribution.  A committed layer: the bottom
+// log2 B levels of its tree are local (a block is a complete subtree); ONE all-to-all then turns the level of M/B
+// digests from round-robin into natural-order blocks -- B times fewer bytes than exchanging the values, and the
+// re-indexing happens inside the next kernel's loads --; the local subtree's root is node G + r of the
+// reference's heap; an all-gather of the G sub-roots (32 B each) and the top log2 G levels + root -> challenge run
+// redundantly on every GPU; the challenge stays in HBM for the next fold.  Below 2^16 values the strictly serial
+// rest of the chain is finished by every rank with the single-GPU chain.
 // Outputs (host, identical on every rank): roots (steps + 1) * 32 B, challenges steps * 4 u64, final
 // coefficients out_coeffs * 4 u64.  Returns the number of folding steps.
 int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, uint32_t out_coeffs,
@@ -380,9 +386,18 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
     ops->h_domain_generator(log_n, omega);
     uint32_t s_, nb_;
     ops->h_constants(mod, one, gen, root, s_, nb_);
-    ops->h_pow(coset_omega, (uint64_t)cm.rank, shift0);  // shift_i = [g] * w_N^i, i = rank + G * t
+    // block size B = 2^blk_log adjacent leaves per rank per round: L / G, at most 8 (the level kernels hash up to 2^3)
+    uint32_t blk_log = log_factor - log_g;
+    if (blk_log > 3 || getenv("HODOR_SHARD_CYCLIC") != nullptr) blk_log = 0;  // B = 1: plain cyclic slices (cosets r, r + G, ..)
+    const uint32_t B = 1u << blk_log;
+    if (blk_log) {
+        ops->h_pow(coset_omega, (uint64_t)cm.rank * B, shift0);  // cosets rank * B + t, t < B
+        step = coset_omega;
+    } else {
+        ops->h_pow(coset_omega, (uint64_t)cm.rank, shift0);  // cosets rank + G * t
+        ops->h_pow(coset_omega, (uint64_t)G, step);
+    }
     if (coset) ops->h_mul(shift0, gen, shift0);
-    ops->h_pow(coset_omega, (uint64_t)G, step);
 
     cudaStream_t st = c->stream;
     const size_t m0 = N >> log_g;  // local slice of layer 0
@@ -406,29 +421,39 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
     uint4* d_roots = top + 2 * 2 * (size_t)G;
     uint4* d_chal = d_roots + 2 * (size_t)(steps + 2);
 
-    rc = ops->ntt(*c, (const uint4*)d_coeffs, val[0], log_n, log_factor - log_g, omega, &shift0, &step, 0, nullptr, st);
+    // with cosets rank*B + t (t < B) the local output d_out[t + B*k] is v[(k*G + rank)*B + t]: the block-cyclic slice
+    rc = ops->ntt(*c, (const uint4*)d_coeffs, val[0], log_n, blk_log ? blk_log : log_factor - log_g, omega, &shift0, &step, 0, nullptr, st);
     if (rc) return rc;
 
     size_t gather_below = (size_t)1 << 16;
-    if (gather_below < 4 * (size_t)G * G) gather_below = 4 * (size_t)G * G;
+    if (gather_below < (size_t)4096 * B * G) gather_below = (size_t)4096 * B * G;  // the level kernels need > 1024 digests per rank
     size_t size = N;
     int layer = 0, cur = 0;
     while (!(size < gather_below || layer >= steps - 1)) {
         const size_t ml = size >> log_g;  // local values of this layer
-        const uint4* leaves = val[cur];
-        if (G > 1) {
+        if (G == 1) {
+            rc = do_merkle(*c, ops, val[cur], ml, nodes, nullptr, nullptr, st);
+        } else if (blk_log == 0) {
+            // exchange the values (cyclic slice -> natural-order block), hash from the received chunks
             rc = all_to_all(cm, val[cur], xbuf, (ml >> log_g) * 32, st);
-            if (rc) return rc;
-            leaves = xbuf;
+            if (!rc) rc = do_merkle(*c, ops, xbuf, ml, nodes, nullptr, nullptr, st, log_g, ml >> log_g);
+        } else {
+            // bottom log2 B levels locally: digest k of this rank is node (M/B) + k*G + rank of the reference's heap
+            const size_t w = ml >> blk_log;  // digests per rank == width of this rank's natural-order block of that level
+            uint4* lvl = nodes + 2 * w;      // scratch heap position [w, 2w) of `nodes`: free until the subtree is built
+            rc = merkle_leaf_blocks(*c, val[cur], ml, (int)blk_log, nodes, st);
+            if (!rc) rc = all_to_all(cm, lvl, xbuf, (w >> log_g) * 32, st);
+            size_t rem = 0;
+            if (!rc) rc = merkle_from_level(*c, xbuf, w, nodes, &rem, st, log_g, w >> log_g);
+            if (!rc) rc = ops->merkle_tail(*c, nodes, nodes, (uint32_t)rem, false, nullptr, nullptr, st);
         }
-        rc = do_merkle(*c, ops, leaves, ml, nodes, nullptr, nullptr, st, G > 1 ? log_g : 0, ml >> log_g);
         if (rc) return rc;
         HODOR_CUDA_TRY(cudaMemsetAsync(top, 0, 2 * (size_t)G * 32, st));
         rc = all_gather(cm, nodes + 2, top + 2 * (size_t)G, 32, st);
         if (rc) return rc;
         rc = ops->merkle_tail(*c, top, top, G, false, d_roots + 2 * layer, d_chal + 2 * layer, st);
         if (rc) return rc;
-        rc = ops->fri_fold(*c, val[cur], ml, log_N, (uint32_t)layer, d_chal + 2 * layer, val[cur ^ 1], (uint64_t)cm.rank, G, st);
+        rc = ops->fri_fold(*c, val[cur], ml, log_N, (uint32_t)layer, d_chal + 2 * layer, val[cur ^ 1], (uint64_t)cm.rank * B, G, blk_log, st);
         if (rc) return rc;
         cur ^= 1;
         size >>= 1;
@@ -440,7 +465,7 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
     if (G > 1) {
         rc = all_gather(cm, val[cur], xbuf, ml * 32, st);
         if (rc) return rc;
-        interleave_kernel<<<(unsigned)((size + 255) / 256 > 1184 ? 1184 : (size + 255) / 256), 256, 0, st>>>(xbuf, nodes, ml, log_g);
+        interleave_kernel<<<(unsigned)((size + 255) / 256 > 1184 ? 1184 : (size + 255) / 256), 256, 0, st>>>(xbuf, nodes, ml, log_g, blk_log);
         HODOR_CUDA_TRY(cudaGetLastError());
         c->launches++;
         full = nodes;
