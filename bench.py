@@ -723,7 +723,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sharded_fri = {"workload": f"coset LDE 2^{LOG_N} -> 2^{LOG_N + s_log_f} + FRI commit chain ({len(res[1])} layers, "
                                f"{len(res[1]) + 1} Merkle trees) sharded over {world} GPU(s)", "ms": s_ms,
                    "lde_elems_per_s": (n << s_log_f) / (s_ms * 1e-3), "scaling": "strong",
-                   "api": "hodor_cuda_lde_fri_sharded (C ABI; NCCL send/recv per committed layer + 32-byte all-gather of sub-roots)",
+                   "api": "hodor_cuda_lde_fri_sharded (C ABI; rank r owns L/G adjacent cosets, folds and the bottom tree levels are local; per "
+                          "committed layer one NCCL send/recv all-to-all of DIGESTS + a 32-byte all-gather of sub-roots)",
                    "nccl_payload_bytes_per_rank": None,
                    "timer": "host perf_counter around the synchronous C-ABI call, barrier + synchronize both sides, max over ranks"}
     b0 = mg.bytes_sent()

@@ -22,6 +22,13 @@ Distribution:
   serial (root -> challenge -> fold), so the layer is all-gathered and finished on every rank with the
   single-GPU chain (hodor_cuda_fri_commit); its first tree is that layer's commitment.
 
+This module is the torch.distributed statement of the algorithm with a pluggable compute backend: what the
+world_size-2/4 gloo tests on the CPU run (oracle as compute double).  The product path is the same algorithm in
+C++ behind the C ABI (`hodor_cuda_lde_fri_sharded`, csrc/sharded.cu; caller: hodor_b200/multigpu.py), which by
+default uses the BLOCK-CYCLIC distribution (`blk_log` > 0 below): rank r computes the B = L/G adjacent cosets
+r*B .. r*B+B-1, so it holds blocks of B adjacent leaves, v[(k*G + r)*B + c]; the bottom log2 B levels of every
+tree are then local and the per-layer all-to-all moves the level of M/B digests instead of the M values.
+
 The result is bit-identical to the single-GPU / reference chain: roots, challenges, final
 coefficients (tests/test_sharded_cpu.py on gloo with the oracle as compute double;
 tests/test_gpu_parity.py::test_sharded_lde_fri_single_gpu emulates all ranks on one GPU).
@@ -125,14 +132,24 @@ def _world(group):
     return 1, 0
 
 
+def block_cyclic_index(t, rank: int, world: int, blk_log: int):
+    """Natural index of local element t when blocks of 2^blk_log adjacent elements are dealt round-robin."""
+    return (((t >> blk_log) * world + rank) << blk_log) | (t & ((1 << blk_log) - 1))
+
+
 def lde_sharded(coeffs: torch.Tensor, log_n: int, log_factor: int, coset: bool, field_id: int, group=None,
-                backend: Optional[FriShardBackend] = None) -> torch.Tensor:
-    """Rank r's cyclic slice v[r + G*tau] of the L-coset LDE; `coeffs` is replicated on every rank."""
+                backend: Optional[FriShardBackend] = None, blk_log: int = 0) -> torch.Tensor:
+    """Rank r's slice of the L-coset LDE; `coeffs` is replicated on every rank.  blk_log 0: the cyclic slice
+    v[r + G*tau] (cosets r, r+G, ..); blk_log = log2(L/G): the block-cyclic slice (cosets r*B .. r*B+B-1)."""
     world, rank = _world(group)
     log_g = world.bit_length() - 1
     if world != 1 << log_g or log_g > log_factor:
         raise ValueError("world size must be a power of two not larger than the blowup factor")
     backend = backend or CudaFriBackend()
+    if blk_log:
+        if blk_log != log_factor - log_g:
+            raise ValueError("block-cyclic sharding needs 2^blk_log == lde_factor / world")
+        return backend.lde_cosets(coeffs, log_n, log_factor, coset, rank << blk_log, 1, blk_log, field_id)
     return backend.lde_cosets(coeffs, log_n, log_factor, coset, rank, world, log_factor - log_g, field_id)
 
 
@@ -182,12 +199,12 @@ class ShardedFriPrototype:
 
 
 def merkle_sharded(block_leaves: torch.Tensor, field_id: int, group=None,
-                   backend: Optional[FriShardBackend] = None):
+                   backend: Optional[FriShardBackend] = None, from_digests: bool = False):
     """Commitment to a layer held as natural-order blocks.  Returns (commitment, challenge tensor); the
     commitment's `top_nodes` / `root` stay tensors until `finalize()` (no host synchronisation here)."""
     world, rank = _world(group)
     backend = backend or CudaFriBackend()
-    nodes = backend.merkle_build(block_leaves, field_id)
+    nodes = backend.tree_from_digests(block_leaves, field_id) if from_digests else backend.merkle_build(block_leaves, field_id)
     sub_root = nodes[1:2].contiguous()
     if world > 1:
         gathered = torch.empty((world, 4), dtype=sub_root.dtype, device=sub_root.device)
@@ -207,7 +224,7 @@ def _digest_bytes(t: torch.Tensor) -> List[bytes]:
 
 def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor: int, out_coeffs: int, field_id: int,
                        group=None, backend: Optional[FriShardBackend] = None, gather_below: int = 1 << 16,
-                       keep_layers: bool = True) -> ShardedFriPrototype:
+                       keep_layers: bool = True, blk_log: int = 0) -> ShardedFriPrototype:
     """NaiveFriIop::proof_from_lde_by_values (src/fri/fri_on_values.rs:11-159) on an LDE held as
     cyclic slices.  Returns roots / challenges / final coefficients identical to the unsharded chain."""
     world, rank = _world(group)
@@ -220,7 +237,7 @@ def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor:
         raise ValueError("local slice has the wrong length")
     proto = ShardedFriPrototype(num_steps=steps)
     values, size, layer = local_cyclic, domain_size, 0
-    gather_below = max(gather_below, 4 * world * world)
+    gather_below = max(gather_below, (4 << blk_log) * world * world)
     pending = []  # (commitment, challenge tensor) of the layers committed while sharded
     while True:
         if size < gather_below or layer >= steps - 1:
@@ -229,21 +246,33 @@ def fri_commit_sharded(local_cyclic: torch.Tensor, domain_size: int, lde_factor:
             if world > 1:
                 parts = [torch.empty_like(values) for _ in range(world)]
                 dist.all_gather(parts, values.contiguous(), group=group)
-                full = torch.stack(parts, dim=1).reshape(size, 4)  # v[r + G*tau] -> natural order
+                if blk_log:  # parts[r][(k << blk_log) | c] = v[((k*G + r) << blk_log) | c]
+                    full = torch.stack([p.view(-1, 1 << blk_log, 4) for p in parts], dim=1).reshape(size, 4)
+                else:
+                    full = torch.stack(parts, dim=1).reshape(size, 4)  # v[r + G*tau] -> natural order
             else:
                 full = values
             t_roots, t_chal, tail_final = backend.fri_commit(full, lde_factor, out_coeffs, field_id)
             proto.roots.extend(bytes(r) for r in t_roots)
             proto.challenges.extend(np.array(c, dtype=np.uint64) for c in t_chal)
             break
-        com, challenge = merkle_sharded(cyclic_to_block(values, group), field_id, group, backend)
+        if blk_log:
+            # bottom log2 B levels locally (a block is a complete subtree), then re-block the DIGESTS
+            digests = backend.leaf_blocks(values, blk_log, field_id)
+            com, challenge = merkle_sharded(cyclic_to_block(digests, group), field_id, group, backend, from_digests=True)
+            com.size = values.shape[0] * world
+        else:
+            com, challenge = merkle_sharded(cyclic_to_block(values, group), field_id, group, backend)
         pending.append((com, challenge))
         if not keep_layers:
             com.local_nodes = None  # let the allocator recycle the subtree
         if keep_layers:
             proto.commitments.append(com)
             proto.layer_slices.append(values)
-        values = backend.fold_shard(values, domain_size, layer, log_g, rank, challenge, field_id)
+        if blk_log:
+            values = backend.fold_shard(values, domain_size, layer, log_g, rank, challenge, field_id, blk_log=blk_log)
+        else:
+            values = backend.fold_shard(values, domain_size, layer, log_g, rank, challenge, field_id)
         size //= 2
         layer += 1
     # one read-back for every sharded layer: roots and challenges, in order, before the tail's

@@ -132,14 +132,30 @@ class OracleFriBackend:
         arr = np.frombuffer(b"".join(t if t else bytes(32) for t in top), np.uint64).reshape(-1, 4)
         return self._t(arr), self._t(O.interpret_hash(field_id, top[1]).reshape(1, 4))
 
-    def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id):
+    def leaf_blocks(self, values, blk_log, field_id):
+        """One digest per block of 2^blk_log adjacent leaves: the root of that block's subtree."""
+        v, B = self._n(values), 1 << blk_log
+        out = [self.O.merkle_create(field_id, np.ascontiguousarray(v[i:i + B]))[1] for i in range(0, v.shape[0], B)]
+        return self._t(np.frombuffer(b"".join(x.tobytes() for x in out), np.uint64).reshape(-1, 4))
+
+    def tree_from_digests(self, digests, field_id):
+        """Heap-ordered tree over a level of digests (root at [1]); the level itself is not stored."""
+        d = [x.tobytes() for x in self._n(digests)]
+        w = len(d)
+        heap = [bytes(32)] * w + d
+        for i in range(w - 1, 0, -1):
+            heap[i] = self.O.hash_node(heap[2 * i], heap[2 * i + 1])
+        return self._t(np.frombuffer(b"".join(heap[:w]), np.uint64).reshape(-1, 4))
+
+    def fold_shard(self, values, initial_domain_size, layer, log_g, rank, challenge, field_id, blk_log=0):
         O, v = self.O, self._n(values)
         if isinstance(challenge, torch.Tensor):
             challenge = self._n(challenge)[0]
         half = v.shape[0] // 2
         log_n0 = initial_domain_size.bit_length() - 1
         winv = O.inverse(field_id, O.domain_generator(field_id, log_n0))
-        tw = np.stack([O.pow_(field_id, winv, (rank + (t << log_g)) << layer) for t in range(half)])
+        from hodor_b200.sharded_fri import block_cyclic_index
+        tw = np.stack([O.pow_(field_id, winv, block_cyclic_index(t, rank, 1 << log_g, blk_log) << layer) for t in range(half)])
         two_inv = O.inverse(field_id, O.to_mont(field_id, O.ints_to_array([2]))[0])
         f0, f1 = v[:half], v[half:]
         odd = O.mul(field_id, O.mul(field_id, O.sub(field_id, f0, f1), tw), np.tile(challenge, (half, 1)))
@@ -156,7 +172,7 @@ class OracleFriBackend:
         return self.O.interpret_hash(field_id, root)
 
 
-def _fri_worker(rank, world, port, log_n, log_factor, out_coeffs, gather_below, result_dir):
+def _fri_worker(rank, world, port, log_n, log_factor, out_coeffs, gather_below, result_dir, blk_log=0):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -166,10 +182,10 @@ def _fri_worker(rank, world, port, log_n, log_factor, out_coeffs, gather_below, 
         from oracle import oracle as O
         be = OracleFriBackend()
         coeffs = O.random_elements(0, 1 << log_n, seed=99)
-        local = lde_sharded(be._t(coeffs), log_n, log_factor, True, 0, backend=be)
+        local = lde_sharded(be._t(coeffs), log_n, log_factor, True, 0, backend=be, blk_log=blk_log)
         block = cyclic_to_block(local)
         proto = fri_commit_sharded(local, (1 << log_n) << log_factor, 1 << log_factor, out_coeffs, 0, backend=be,
-                                   gather_below=gather_below)
+                                   gather_below=gather_below, blk_log=blk_log)
         np.savez(os.path.join(result_dir, f"fri{rank}.npz"), local=be._n(local), block=be._n(block),
                  roots=np.frombuffer(b"".join(proto.roots), np.uint8), challenges=np.stack(proto.challenges),
                  final=proto.final_coefficients, sharded_layers=len(proto.commitments))
@@ -196,3 +212,33 @@ def test_sharded_lde_and_fri_chain_over_gloo(oracle, tmp_path, world, log_n, log
         assert np.array_equal(res["final"], want.final_coefficients)
         if gather_below <= 64:
             assert int(res["sharded_layers"]) >= 2  # several layers really ran distributed
+
+
+@pytest.mark.parametrize("world,log_n,log_factor,gather_below", [(2, 5, 3, 16), (4, 6, 3, 64), (2, 5, 1, 16)])
+def test_block_cyclic_sharded_chain_over_gloo(oracle, tmp_path, world, log_n, log_factor, gather_below):
+    """The distribution the C++ product path uses (csrc/sharded.cu): rank r owns the B = L/G adjacent cosets, holds
+    blocks of B adjacent leaves, hashes the bottom log2 B tree levels locally and exchanges DIGESTS; folds stay local."""
+    from hodor_b200.sharded_fri import block_cyclic_index
+    out_coeffs = 2
+    blk_log = log_factor - (world.bit_length() - 1)
+    mp.spawn(_fri_worker, args=(world, _free_port(), log_n, log_factor, out_coeffs, gather_below, str(tmp_path), blk_log),
+             nprocs=world, join=True)
+    coeffs = oracle.random_elements(0, 1 << log_n, seed=99)
+    L = 1 << log_factor
+    full = oracle.lde(0, coeffs, log_n, L, True)
+    want = oracle.fri_commit(0, full, L, out_coeffs)
+    m = full.shape[0] // world
+    for r in range(world):
+        res = np.load(tmp_path / f"fri{r}.npz")
+        idx = [block_cyclic_index(t, r, world, blk_log) for t in range(m)]
+        assert np.array_equal(res["local"], full[idx])  # block-cyclic slice, no communication
+        assert res["roots"].tobytes() == b"".join(want.roots())
+        assert np.array_equal(res["challenges"], want.challenges)
+        assert np.array_equal(res["final"], want.final_coefficients)
+        assert int(res["sharded_layers"]) >= 1
+    # fold pairs stay on one rank and land on the same distribution one layer down
+    M = full.shape[0]
+    for r in range(world):
+        for t in range(m // 2):
+            i = block_cyclic_index(t, r, world, blk_log)
+            assert block_cyclic_index(t + m // 2, r, world, blk_log) == i + M // 2 and i < M // 2
