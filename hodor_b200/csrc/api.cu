@@ -316,7 +316,11 @@ int hodor_cuda_init(int device) {
     }
     std::unique_ptr<Ctx> c(new Ctx());
     c->device = device;
-    HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    HODOR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    HODOR_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+    HODOR_CUDA_TRY(cudaStreamCreateWithPriority(&c->commit_stream, cudaStreamNonBlocking, prio_least));
+    if (const char* e = getenv("HODOR_CONCURRENT_COMMIT")) c->concurrent_commit = atoi(e) != 0;
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaMalloc((void**)&c->small, 4096));
@@ -364,6 +368,7 @@ void hodor_cuda_shutdown(void) {
         if (g_ctx->stage_free[b]) cudaEventDestroy(g_ctx->stage_free[b]);
     }
     cudaStreamDestroy(g_ctx->stream);
+    if (g_ctx->commit_stream) cudaStreamDestroy(g_ctx->commit_stream);
     cudaStreamDestroy(g_ctx->copy_in);
     cudaStreamDestroy(g_ctx->copy_out);
     delete g_ctx;
@@ -1013,6 +1018,10 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
         cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming);
     }
     const bool roots_pinned = roots != nullptr && (size_t)count * 32 <= Ctx::PINNED_SMALL_BYTES;
+    const bool overlap = c->concurrent_commit && count > 1 && total >= ((size_t)1 << 20);
+    cudaEvent_t lde_done[2] = {nullptr, nullptr};
+    if (overlap)
+        for (auto& ev : lde_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     auto step = [&](uint32_t i) -> int {
         hodor_tree* t = tree_alloc(c, field_id, total, true);
         if (!t) return HODOR_ERR_OOM;
@@ -1029,17 +1038,32 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
         int r = do_lde(*c, ops, src, (uint4*)t->values, log_n, log_factor, coset, c->stream);
         if (r) return r;
         if (!coeffs_on_device) HODOR_CUDA_TRY(cudaEventRecord(comp_done[i % nbuf], c->stream));
-        r = do_merkle(*c, ops, t->values, total, t->nodes, t->root, t->chal, c->stream);
+        // the tree: beside the next polynomial's transform when there is one (see Ctx::commit_stream)
+        cudaStream_t ts = c->stream;
+        if (overlap) {
+            HODOR_CUDA_TRY(cudaEventRecord(lde_done[i % 2], c->stream));
+            HODOR_CUDA_TRY(cudaStreamWaitEvent(c->commit_stream, lde_done[i % 2], 0));
+            ts = c->commit_stream;
+            c->merkle_backfill = true;
+        }
+        r = do_merkle(*c, ops, t->values, total, t->nodes, t->root, t->chal, ts);
+        c->merkle_backfill = false;
         if (r) return r;
         if (roots) {  // via pinned scratch while it lasts: see Ctx::pinned_small
             uint8_t* dst = roots_pinned ? c->pinned_small + 32 * (size_t)i : roots + 32 * (size_t)i;
-            HODOR_CUDA_TRY(cudaMemcpyAsync(dst, t->root, 32, cudaMemcpyDeviceToHost, c->stream));
+            HODOR_CUDA_TRY(cudaMemcpyAsync(dst, t->root, 32, cudaMemcpyDeviceToHost, ts));
         }
         return HODOR_OK;
     };
     for (uint32_t i = 0; i < count && rc == HODOR_OK; i++) rc = step(i);
     cudaStreamSynchronize(c->copy_in);
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (overlap) {
+        const cudaError_t e2 = cudaStreamSynchronize(c->commit_stream);
+        if (e == cudaSuccess) e = e2;
+        for (auto& ev : lde_done)
+            if (ev) cudaEventDestroy(ev);
+    }
     for (uint32_t b = 0; b < nbuf; b++) {
         if (in_done[b]) cudaEventDestroy(in_done[b]);
         if (comp_done[b]) cudaEventDestroy(comp_done[b]);

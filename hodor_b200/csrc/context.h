@@ -58,6 +58,13 @@ struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined batch entry points
+    // Lift-and-commit of several polynomials: the tree of polynomial i is hashed on this LOW-priority stream while the
+    // transform of polynomial i+1 runs on `stream` (high priority).  The transform is bound by the multiplier pipe
+    // (76 % busy, ALU 41 %), the hashing by the ALU pipe (88 %, multiplier 60 %): sharing SMs lets each use the issue
+    // slots and the pipe the other leaves idle.  HODOR_CONCURRENT_COMMIT=0 puts both on one stream.
+    cudaStream_t commit_stream = nullptr;
+    bool concurrent_commit = true;
+    bool merkle_backfill = false;  // set around the tree builds that run beside a transform
     std::mutex mu;
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -229,8 +236,8 @@ const FieldOps* field_ops(int field_id);
 int merkle_levels(Ctx&, const uint4* leaves, size_t n, uint4* nodes, size_t* remaining_width, cudaStream_t st,
                   uint32_t leaf_log_g = 0, size_t leaf_chunk = 0);
 int merkle_upper_levels(Ctx&, uint4* nodes, size_t w, size_t* remaining_width, cudaStream_t st);
-// bottom k (1..3) levels only: leaves -> the level of n >> k nodes, written at heap[(n >> k), 2 (n >> k))
-int merkle_leaf_blocks(Ctx&, const uint4* leaves, size_t n, int k, uint4* heap, cudaStream_t st);
+// out[g] = root of the subtree over leaves [g << k, (g + 1) << k), k in 1..3
+int merkle_block_roots(Ctx&, const uint4* leaves, size_t blocks, int k, uint4* out, cudaStream_t st);
 // the tree above a level of w digests given in `level` (natural order, or 2^log_g cyclic chunks of `chunk` digests):
 // writes heap [.., w) down to the tail width; *remaining_width as merkle_levels
 int merkle_from_level(Ctx&, const uint4* level, size_t w, uint4* nodes, size_t* remaining_width, cudaStream_t st,

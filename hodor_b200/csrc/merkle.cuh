@@ -267,6 +267,26 @@ DEV Digest merkle_subtree_fn(const B2sState& key, uint4* nodes, size_t w_in, siz
     }
 }
 
+// Root of the complete subtree over the 2^K adjacent leaves starting at `first`; nothing below it is stored.
+template <int K>
+DEV Digest merkle_block_root(const B2sState& key, const uint4* in, size_t first) {
+    if constexpr (K == 0) {
+        return tree_hash_leaf(key, ld_digest(in, first));
+    } else {
+        const Digest l = merkle_block_root<K - 1>(key, in, first);
+        const Digest r = merkle_block_root<K - 1>(key, in, first + ((size_t)1 << (K - 1)));
+        return tree_hash_node(key, l, r);
+    }
+}
+// out[g] = root of leaves [g * 2^K, (g + 1) * 2^K): the level a rank of the sharded chain can hash without its
+// neighbours' leaves (it holds blocks of 2^K adjacent ones) and then exchanges instead of the values
+template <int K>
+__global__ void __launch_bounds__(256) merkle_block_roots_kernel(const uint4* in, uint4* out, size_t blocks,
+                                                                 const __grid_constant__ B2sState key) {
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < blocks; g += (size_t)gridDim.x * blockDim.x)
+        st_digest(out, g, merkle_block_root<K>(key, in, g << K));
+}
+
 // grid-stride over groups of 2^K inputs; writes K node levels
 template <int K, bool LEAF>
 __global__ void __launch_bounds__(256) merkle_levels_kernel(const uint4* in, uint4* nodes, size_t w_in,

@@ -18,10 +18,24 @@ template <int K, bool LEAF>
 static int launch_levels(Ctx& c, const uint4* in, uint4* nodes, size_t w_in, cudaStream_t st, LeafMap lm = LeafMap{0, 0}) {
     // small levels: narrow blocks, so that a few thousand subtrees still spread over many SMs
     const size_t groups = w_in >> K;
-    const unsigned block = groups >= 148 * 256 ? 256 : (groups >= 148 * 64 ? 128 : 32);
+    unsigned block = groups >= 148 * 256 ? 256 : (groups >= 148 * 64 ? 128 : 32);
+    unsigned grid = grid_for(groups, block);
+    if (c.merkle_backfill && groups >= 148 * 256) {
+        // Running beside a transform (Ctx::merkle_backfill): small, short-lived blocks -- 128 threads x 80 registers
+        // fit into what three resident pass-kernel blocks leave free on an SM, need no shared memory, and return
+        // their slot after one subtree per thread, so the block scheduler can keep the transform's blocks (higher
+        // stream priority) resident and fill the gaps with hashing.
+        block = 128;
+        grid = (unsigned)((groups + block - 1) / block);
+        auto kern = merkle_levels_kernel<K, LEAF>;
+        if (!c.configured_kernels.count((const void*)kern)) {  // same L1 / shared split as the pass kernels it shares SMs with
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            c.configured_kernels.insert((const void*)kern);
+        }
+    }
     {
         ProfScope ps(c, st, LEAF ? "merkle_levels_leaf" : "merkle_levels_node");
-        merkle_levels_kernel<K, LEAF><<<grid_for(groups, block), block, 0, st>>>(in, nodes, w_in, c.key, lm);
+        merkle_levels_kernel<K, LEAF><<<grid, block, 0, st>>>(in, nodes, w_in, c.key, lm);
     }
     HODOR_CUDA_TRY(cudaGetLastError());
     return HODOR_OK;
@@ -83,14 +97,21 @@ int merkle_upper_levels(Ctx& c, uint4* nodes, size_t w, size_t* remaining_width,
 
 size_t merkle_tail_width() { return tail_max(); }
 
-int merkle_leaf_blocks(Ctx& c, const uint4* leaves, size_t n, int k, uint4* heap, cudaStream_t st) {
-    if ((n >> k) == 0) return fail(HODOR_ERR_INVALID_ARG, "internal: leaf blocks larger than the vector");
-    switch (k) {
-        case 1: return launch_levels<1, true>(c, leaves, heap, n, st);
-        case 2: return launch_levels<2, true>(c, leaves, heap, n, st);
-        case 3: return launch_levels<3, true>(c, leaves, heap, n, st);
+int merkle_block_roots(Ctx& c, const uint4* leaves, size_t blocks, int k, uint4* out, cudaStream_t st) {
+    if (blocks == 0) return HODOR_OK;
+    const unsigned block = blocks >= 148 * 256 ? 256 : (blocks >= 148 * 64 ? 128 : 32);
+    const unsigned grid = grid_for(blocks, block);
+    {
+        ProfScope ps(c, st, "merkle_block_roots");
+        switch (k) {
+            case 1: merkle_block_roots_kernel<1><<<grid, block, 0, st>>>(leaves, out, blocks, c.key); break;
+            case 2: merkle_block_roots_kernel<2><<<grid, block, 0, st>>>(leaves, out, blocks, c.key); break;
+            case 3: merkle_block_roots_kernel<3><<<grid, block, 0, st>>>(leaves, out, blocks, c.key); break;
+            default: return fail(HODOR_ERR_INVALID_ARG, "internal: leaf block size must be 2, 4 or 8");
+        }
     }
-    return fail(HODOR_ERR_INVALID_ARG, "internal: leaf block size must be 2, 4 or 8");
+    HODOR_CUDA_TRY(cudaGetLastError());
+    return HODOR_OK;
 }
 
 int merkle_from_level(Ctx& c, const uint4* level, size_t w, uint4* nodes, size_t* remaining_width, cudaStream_t st,

@@ -81,6 +81,7 @@ struct Comm {
     size_t peer_bytes = 0;              // size the mappings were made for (0: none)
     int peer_state = 0;                 // 0 untried, 1 mapped, -1 unavailable (fall back to NCCL send/recv)
     uint4* flag = nullptr;              // 64 B of device scratch for the barrier collectives
+    cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};  // compute stream <-> exchange stream of the pipelined layers
     int ensure(int which, size_t bytes) {
         if (bytes <= buf_bytes[which]) return HODOR_OK;
         if (buf[which]) {
@@ -107,6 +108,8 @@ void comm_destroy(Ctx* c) {
     cudaDeviceSynchronize();
     close_peers(*c->comm);
     if (c->comm->flag) cudaFree(c->comm->flag);
+    for (auto ev : c->comm->pipe_ev)
+        if (ev) cudaEventDestroy(ev);
     if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
     for (int i = 0; i < 2; i++)
         if (c->comm->buf[i]) cudaFree(c->comm->buf[i]);
@@ -440,11 +443,44 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
         } else {
             // bottom log2 B levels locally: digest k of this rank is node (M/B) + k*G + rank of the reference's heap
             const size_t w = ml >> blk_log;  // digests per rank == width of this rank's natural-order block of that level
-            uint4* lvl = nodes + 2 * w;      // scratch heap position [w, 2w) of `nodes`: free until the subtree is built
-            rc = merkle_leaf_blocks(*c, val[cur], ml, (int)blk_log, nodes, st);
-            if (!rc) rc = all_to_all(cm, lvl, xbuf, (w >> log_g) * 32, st);
+            const size_t wc = w >> log_g;    // digests per destination
+            uint4* lvl = nodes + 2 * w;      // position [w, 2w) of `nodes`: free until the subtree above is built
+            if (wc >= ((size_t)1 << 15) && getenv("HODOR_SHARD_NO_PIPELINE") == nullptr) {
+                // pipelined by destination: the digests for rank (r + s) % G are hashed while those of step s - 1
+                // travel (pairwise send / recv on a second stream: at step s every rank sends to r + s and
+                // receives from r - s)
+                cudaStream_t cs = c->copy_in;
+                if (!cm.pipe_ev[0])
+                    for (auto& ev : cm.pipe_ev) HODOR_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                HODOR_CUDA_TRY(cudaEventRecord(cm.pipe_ev[0], st));  // xbuf's previous readers are done
+                HODOR_CUDA_TRY(cudaStreamWaitEvent(cs, cm.pipe_ev[0], 0));
+                for (uint32_t s = 0; s < G && !rc; s++) {
+                    const uint32_t to = ((uint32_t)cm.rank + s) % G, from = ((uint32_t)cm.rank + G - s) % G;
+                    rc = merkle_block_roots(*c, val[cur] + 2 * ((size_t)to * wc << blk_log), wc, (int)blk_log, lvl + 2 * (size_t)to * wc, st);
+                    if (rc) break;
+                    HODOR_CUDA_TRY(cudaEventRecord(cm.pipe_ev[1], st));
+                    HODOR_CUDA_TRY(cudaStreamWaitEvent(cs, cm.pipe_ev[1], 0));
+                    if (s == 0) {
+                        HODOR_CUDA_TRY(cudaMemcpyAsync(xbuf + 2 * (size_t)cm.rank * wc, lvl + 2 * (size_t)cm.rank * wc, wc * 32,
+                                                       cudaMemcpyDeviceToDevice, cs));
+                    } else {
+                        HODOR_NCCL_TRY(g_nccl.GroupStart());
+                        HODOR_NCCL_TRY(g_nccl.Send(lvl + 2 * (size_t)to * wc, wc * 32, ncclUint8, (int)to, cm.comm, cs));
+                        HODOR_NCCL_TRY(g_nccl.Recv(xbuf + 2 * (size_t)from * wc, wc * 32, ncclUint8, (int)from, cm.comm, cs));
+                        HODOR_NCCL_TRY(g_nccl.GroupEnd());
+                        cm.bytes_sent += wc * 32;
+                    }
+                }
+                if (!rc) {
+                    HODOR_CUDA_TRY(cudaEventRecord(cm.pipe_ev[2], cs));
+                    HODOR_CUDA_TRY(cudaStreamWaitEvent(st, cm.pipe_ev[2], 0));
+                }
+            } else {
+                rc = merkle_block_roots(*c, val[cur], w, (int)blk_log, lvl, st);
+                if (!rc) rc = all_to_all(cm, lvl, xbuf, wc * 32, st);
+            }
             size_t rem = 0;
-            if (!rc) rc = merkle_from_level(*c, xbuf, w, nodes, &rem, st, log_g, w >> log_g);
+            if (!rc) rc = merkle_from_level(*c, xbuf, w, nodes, &rem, st, log_g, wc);
             if (!rc) rc = ops->merkle_tail(*c, nodes, nodes, (uint32_t)rem, false, nullptr, nullptr, st);
         }
         if (rc) return rc;

@@ -1,0 +1,46 @@
+"""Same-session A/B of lift-and-commit (hodor_cuda_lde_commit_batch, 2^24 x 8, 8 polynomials per call, pinned host
+coefficients): ms per polynomial.  Variants through the library's environment switches, one process each:
+    HODOR_CONCURRENT_COMMIT=0 python tools/commit_ab.py   # tree of polynomial i after its LDE, on one stream
+    python tools/commit_ab.py                             # tree of polynomial i beside the LDE of polynomial i+1"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import hodor_b200 as H
+from hodor_b200 import _ffi
+
+H.init(0)
+lib = _ffi.lib
+n, count = 1 << 24, 8
+rng = np.random.default_rng(1)
+a = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+a[:, 3] = rng.integers(0, 0x73EDA753299D7D48, size=n, dtype=np.uint64)
+h_in = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
+h_in.numpy().view(np.uint64)[:] = a
+
+
+def chunk():
+    ins = (C.c_void_p * count)(*[h_in.data_ptr()] * count)
+    outs = (C.c_void_p * count)()
+    roots = np.zeros((count, 32), np.uint8)
+    _ffi.check(lib.hodor_cuda_lde_commit_batch(ins, count, 24, 3, 1, 0, outs, roots.ctypes.data_as(_ffi.u8p), 0))
+    for i in range(count):
+        lib.hodor_cuda_tree_free(outs[i])
+    return roots
+
+
+r0 = chunk()
+t0 = time.perf_counter()
+reps = 3
+for _ in range(reps):
+    r = chunk()
+ms = (time.perf_counter() - t0) * 1e3 / (reps * count)
+assert all(r[i].tobytes() == r0[0].tobytes() for i in range(count))
+print(json.dumps({"bench": "lde_commit_batch 2^24 x 8", "concurrent_commit": os.environ.get("HODOR_CONCURRENT_COMMIT", "1"),
+                  "ms_per_polynomial": ms, "root": r0[0].tobytes().hex()}))
