@@ -445,10 +445,11 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
             const size_t w = ml >> blk_log;  // digests per rank == width of this rank's natural-order block of that level
             const size_t wc = w >> log_g;    // digests per destination
             uint4* lvl = nodes + 2 * w;      // position [w, 2w) of `nodes`: free until the subtree above is built
-            if (wc >= ((size_t)1 << 15) && getenv("HODOR_SHARD_NO_PIPELINE") == nullptr) {
-                // pipelined by destination: the digests for rank (r + s) % G are hashed while those of step s - 1
-                // travel (pairwise send / recv on a second stream: at step s every rank sends to r + s and
-                // receives from r - s)
+            if (wc >= ((size_t)1 << 15) && getenv("HODOR_SHARD_PIPELINE") != nullptr) {
+                // OFF by default (measured on 8 GPUs: 24.5 ms against 16.4 ms for the single grouped all-to-all below --
+                // G pairwise steps cost more than they hide; profiles/r02_experiments.md).  Pipelined by destination:
+                // the digests for rank (r + s) % G are hashed while those of step s - 1 travel (pairwise send / recv
+                // on a second stream: at step s every rank sends to r + s and receives from r - s)
                 cudaStream_t cs = c->copy_in;
                 if (!cm.pipe_ev[0])
                     for (auto& ev : cm.pipe_ev) HODOR_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
