@@ -192,9 +192,27 @@ struct Ops {
         auto it = c.ntt_tables.find(key);
         if (it == c.ntt_tables.end()) {
             NttTables t;
+            Fe* d_base = nullptr;  // device copy of the per-B bases
+            struct Guard {  // an early return below must not leak what was already allocated for `t`
+                Ctx& c;
+                NttTables& t;
+                Fe*& d_base;
+                bool keep = false, pw_counted = false;
+                ~Guard() {
+                    if (d_base) cudaFree(d_base);
+                    if (keep) return;
+                    if (t.pw.block) {
+                        cudaFree(t.pw.block);
+                        if (pw_counted) c.table_bytes -= t.pw.bytes;  // build_pow_tables adds them only when it succeeds
+                    }
+                    if (t.tw_b_block) cudaFree(t.tw_b_block);
+                    if (t.tw_direct_block) cudaFree(t.tw_direct_block);
+                }
+            } guard{c, t, d_base};
             std::vector<Fe> base{omega};
             int rc = build_pow_tables(c, t.pw, base, log_n == 0 ? 1 : log_n, nullptr, st);
             if (rc) return rc;
+            guard.pw_counted = true;
             if (log_n >= 4) {
                 Fld f;
                 const Fe w16 = pow2k(omega, log_n - 4);
@@ -213,7 +231,6 @@ struct Ops {
                     if (need[b]) total += (size_t)1 << b;
                 t.bytes = total * sizeof(FePre);
                 HODOR_CUDA_TRY(cudaMalloc((void**)&t.tw_b_block, t.bytes));
-                Fe* d_base = nullptr;  // device copy of the per-B bases
                 HODOR_CUDA_TRY(cudaMalloc((void**)&d_base, 4 * sizeof(Fe)));
                 uint4* cur = t.tw_b_block;
                 Fe hb[4];
@@ -269,9 +286,9 @@ struct Ops {
                     HODOR_CUDA_TRY(cudaGetLastError());
                     t.bytes += dtotal * sizeof(FePre);
                 }
-                cudaFree(d_base);
                 c.table_bytes += t.bytes;
             }
+            guard.keep = true;
             it = c.ntt_tables.emplace(key, t).first;
         }
         *out = &it->second;
