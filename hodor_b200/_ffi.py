@@ -132,6 +132,14 @@ _SIGS = {
     "hodor_cuda_lde_cosets_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                             C.c_int, vp]),
     "hodor_cuda_distribute_powers_dev": (C.c_int, [vp, C.c_uint64, u64p, C.c_int, vp]),
+    "hodor_cuda_precomputed_omegas_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_int, vp]),
+    "hodor_cuda_precomputed_omegas": (C.c_int, [u64p, u64p, u64p, C.c_uint32, C.c_int]),
+    "hodor_cuda_ali_dense_inverse_divisor": (C.c_int, [u64p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                       C.POINTER(C.c_uint64), C.c_int]),
+    "hodor_cuda_ali_boundary_inverse_divisor": (C.c_int, [u64p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]),
+    "hodor_cuda_ali_dense_inverse_divisor_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                           C.POINTER(C.c_uint64), C.c_int, vp]),
+    "hodor_cuda_ali_boundary_inverse_divisor_dev": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, vp]),
     "hodor_cuda_elementwise_dev": (C.c_int, [C.c_int, vp, vp, vp, C.c_uint64, C.c_int, vp]),
     "hodor_cuda_poly_op_dev": (C.c_int, [C.c_int, vp, vp, u64p, C.c_uint64, vp, C.c_uint64, C.c_int, vp]),
     "hodor_cuda_batch_inversion_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),

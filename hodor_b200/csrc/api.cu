@@ -645,6 +645,159 @@ int hodor_cuda_distribute_powers_dev(void* d_a, uint64_t n, const uint64_t g[4],
     if (n == 0) return HODOR_OK;
     return ops->scale_pow(*c, (uint4*)d_a, (size_t)n, fe_from_u64(g), pick_stream(c, stream));
 }
+// ---- setup work of Prover::new on the device: twiddle vectors and the ALI inverse divisors ------------------------
+static int precomputed_omegas_impl(Ctx* c, const FieldOps* ops, void* d_omegas, void* d_coset, void* d_omegas_inv,
+                                   uint32_t log_n, cudaStream_t st) {
+    if (log_n > 40) return fail(HODOR_ERR_DOMAIN, "precomputed_omegas: domain too large");
+    Fe omega, omega_inv, modulus, one, gen, root;
+    uint32_t s2 = 0, bits = 0;
+    if (ops->h_domain_generator(log_n, omega)) return fail(HODOR_ERR_DOMAIN, "precomputed_omegas: size exceeds the field's 2-adicity");
+    ops->h_constants(modulus, one, gen, root, s2, bits);
+    if (ops->h_inverse(omega, omega_inv)) return fail(HODOR_ERR_NOT_INVERTIBLE, "precomputed_omegas: generator not invertible");
+    const size_t n = (size_t)1 << log_n;
+    int rc = HODOR_OK;
+    if (d_omegas) rc = ops->coset_map(*c, 0, (uint4*)d_omegas, n, omega, one, nullptr, nullptr, 0, nullptr, 0, st);
+    if (!rc && d_coset) rc = ops->coset_map(*c, 0, (uint4*)d_coset, n, omega, gen, nullptr, nullptr, 0, nullptr, 0, st);
+    if (!rc && d_omegas_inv) rc = ops->coset_map(*c, 0, (uint4*)d_omegas_inv, n / 2, omega_inv, one, nullptr, nullptr, 0, nullptr, 0, st);
+    return rc;
+}
+static int ali_dense_impl(Ctx* c, const FieldOps* ops, void* d_out, uint32_t log_column, uint32_t log_evaluation,
+                          uint64_t start_at, uint64_t span, uint64_t num_rows, uint64_t* divisor_degree, cudaStream_t st) {
+    if (d_out == nullptr) return fail(HODOR_ERR_INVALID_ARG, "ali_dense_inverse_divisor: d_out is NULL");
+    if (log_column > 40 || log_evaluation > 40 || log_evaluation < log_column)
+        return fail(HODOR_ERR_INVALID_ARG, "ali_dense_inverse_divisor: need column domain <= evaluation domain");
+    const uint64_t T = 1ull << log_column, E = 1ull << log_evaluation;
+    // the reference's usize subtractions (src/ali/per_register/mod.rs:71-75) would underflow (debug panic) otherwise
+    if (num_rows > T || span > num_rows || start_at > num_rows - span)
+        return fail(HODOR_ERR_INVALID_ARG, "ali_dense_inverse_divisor: start_at + span must fit into num_rows <= column domain");
+    const uint64_t num_roots = start_at + (T - (num_rows - span));
+    if (num_roots > (1u << 20)) return fail(HODOR_ERR_INVALID_ARG, "ali_dense_inverse_divisor: more than 2^20 excluded rows");
+    Fe w_col, w_eval, modulus, one, gen, root;
+    uint32_t s2 = 0, bits = 0;
+    if (ops->h_domain_generator(log_column, w_col) || ops->h_domain_generator(log_evaluation, w_eval))
+        return fail(HODOR_ERR_DOMAIN, "ali_dense_inverse_divisor: size exceeds the field's 2-adicity");
+    ops->h_constants(modulus, one, gen, root, s2, bits);
+    // roots of the divisor's numerator: omega^k, k in [0, start_at) and [num_rows - span, T)   (:77-93)
+    std::vector<Fe> roots;
+    roots.reserve((size_t)num_roots);
+    Fe r = one;
+    for (uint64_t k = 0; k < start_at; k++) {
+        roots.push_back(r);
+        ops->h_mul(r, w_col, r);
+    }
+    ops->h_pow(w_col, num_rows - span, r);
+    for (uint64_t k = num_rows - span; k < T; k++) {
+        roots.push_back(r);
+        ops->h_mul(r, w_col, r);
+    }
+    // x_j^T - 1 on the coset g * <w_eval>: g^T * (w_eval^T)^j, w_eval^T of order E/T -> E/T distinct values   (:112-130)
+    const uint64_t L = E / T;
+    std::vector<Fe> inv_van((size_t)L);
+    Fe gT, wL, cur;
+    ops->h_pow(gen, T, gT);
+    ops->h_pow(w_eval, T, wL);
+    cur = gT;
+    for (uint64_t k = 0; k < L; k++) {
+        Fe v;
+        ops->h_sub(cur, one, v);
+        if (ops->h_inverse(v, inv_van[(size_t)k]))
+            return fail(HODOR_ERR_NOT_INVERTIBLE, "ali_dense_inverse_divisor: X^T - 1 vanishes on the evaluation coset");
+        ops->h_mul(cur, wL, cur);
+    }
+    if (divisor_degree) *divisor_degree = T - start_at - (T - num_rows) - span;
+    return ops->coset_map(*c, 2, (uint4*)d_out, (size_t)E, w_eval, gen, nullptr, roots.data(), (uint32_t)roots.size(), inv_van.data(),
+                          (uint32_t)L, st);
+}
+static int ali_boundary_impl(Ctx* c, const FieldOps* ops, void* d_out, uint32_t log_column, uint32_t log_evaluation,
+                             uint64_t row, cudaStream_t st) {
+    if (d_out == nullptr) return fail(HODOR_ERR_INVALID_ARG, "ali_boundary_inverse_divisor: d_out is NULL");
+    if (log_column > 40 || log_evaluation > 40) return fail(HODOR_ERR_INVALID_ARG, "ali_boundary_inverse_divisor: domain too large");
+    Fe w_col, w_eval, modulus, one, gen, root, at;
+    uint32_t s2 = 0, bits = 0;
+    if (ops->h_domain_generator(log_column, w_col) || ops->h_domain_generator(log_evaluation, w_eval))
+        return fail(HODOR_ERR_DOMAIN, "ali_boundary_inverse_divisor: size exceeds the field's 2-adicity");
+    ops->h_constants(modulus, one, gen, root, s2, bits);
+    ops->h_pow(w_col, row, at);
+    const size_t n = (size_t)1 << log_evaluation;
+    int rc = ops->coset_map(*c, 1, (uint4*)d_out, n, w_eval, gen, &at, nullptr, 0, nullptr, 0, st);
+    if (rc) return rc;
+    int* d_status = (int*)(c->small + 64);
+    rc = ops->batch_inversion(*c, (uint4*)d_out, n, d_status, st);
+    if (rc) return rc;
+    int* status = (int*)c->pinned_small;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+    if (*status != 0) return fail(HODOR_ERR_NOT_INVERTIBLE, "ali_boundary_inverse_divisor: X - omega^row vanishes on the coset");
+    return HODOR_OK;
+}
+int hodor_cuda_precomputed_omegas_dev(void* d_omegas, void* d_coset, void* d_omegas_inv, uint32_t log_n, int field_id,
+                                      void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return precomputed_omegas_impl(c, ops, d_omegas, d_coset, d_omegas_inv, log_n, pick_stream(c, stream));
+}
+int hodor_cuda_ali_dense_inverse_divisor_dev(void* d_out, uint32_t log_column, uint32_t log_evaluation, uint64_t start_at,
+                                             uint64_t span, uint64_t num_rows, uint64_t* divisor_degree, int field_id,
+                                             void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return ali_dense_impl(c, ops, d_out, log_column, log_evaluation, start_at, span, num_rows, divisor_degree, pick_stream(c, stream));
+}
+int hodor_cuda_ali_boundary_inverse_divisor_dev(void* d_out, uint32_t log_column, uint32_t log_evaluation, uint64_t row,
+                                                int field_id, void* stream) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    return ali_boundary_impl(c, ops, d_out, log_column, log_evaluation, row, pick_stream(c, stream));
+}
+// host-vector forms (what a Rust caller holding Vec<F> binds): computed in the library's I/O buffer, copied out
+int hodor_cuda_precomputed_omegas(uint64_t* omegas, uint64_t* coset, uint64_t* omegas_inv, uint32_t log_n, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (log_n > 34) return fail(HODOR_ERR_DOMAIN, "precomputed_omegas: domain too large");
+    const size_t n = (size_t)1 << log_n;
+    int rc = c->ensure_io(0, n * 32);
+    if (rc) return rc;
+    uint64_t* outs[3] = {omegas, coset, omegas_inv};
+    for (int k = 0; k < 3; k++) {
+        if (!outs[k]) continue;
+        const size_t cnt = k == 2 ? n / 2 : n;
+        if (cnt == 0) continue;
+        rc = precomputed_omegas_impl(c, ops, k == 0 ? c->io[0] : nullptr, k == 1 ? c->io[0] : nullptr, k == 2 ? c->io[0] : nullptr,
+                                     log_n, c->stream);
+        if (rc) return rc;
+        HODOR_CUDA_TRY(cudaMemcpyAsync(outs[k], c->io[0], cnt * 32, cudaMemcpyDeviceToHost, c->stream));
+        HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return HODOR_OK;
+}
+int hodor_cuda_ali_dense_inverse_divisor(uint64_t* out, uint32_t log_column, uint32_t log_evaluation, uint64_t start_at,
+                                         uint64_t span, uint64_t num_rows, uint64_t* divisor_degree, int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (out == nullptr || log_evaluation > 34) return fail(HODOR_ERR_INVALID_ARG, "ali_dense_inverse_divisor: bad output / domain too large");
+    const size_t bytes = ((size_t)1 << log_evaluation) * 32;
+    int rc = c->ensure_io(0, bytes);
+    if (rc) return rc;
+    rc = ali_dense_impl(c, ops, c->io[0], log_column, log_evaluation, start_at, span, num_rows, divisor_degree, c->stream);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[0], bytes, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
+int hodor_cuda_ali_boundary_inverse_divisor(uint64_t* out, uint32_t log_column, uint32_t log_evaluation, uint64_t row,
+                                            int field_id) {
+    LOCKED_CTX();
+    GET_OPS(field_id);
+    if (out == nullptr || log_evaluation > 34) return fail(HODOR_ERR_INVALID_ARG, "ali_boundary_inverse_divisor: bad output / domain too large");
+    const size_t bytes = ((size_t)1 << log_evaluation) * 32;
+    int rc = c->ensure_io(0, bytes);
+    if (rc) return rc;
+    rc = ali_boundary_impl(c, ops, c->io[0], log_column, log_evaluation, row, c->stream);
+    if (rc) return rc;
+    HODOR_CUDA_TRY(cudaMemcpyAsync(out, c->io[0], bytes, cudaMemcpyDeviceToHost, c->stream));
+    HODOR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HODOR_OK;
+}
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,
                                void* stream) {
     LOCKED_CTX();

@@ -214,6 +214,10 @@ struct FieldOps {
     int (*scale_pow)(Ctx&, uint4* a, size_t n, const Fe& g, cudaStream_t st);
     int (*elementwise)(Ctx&, int op, const uint4* a, const uint4* b, uint4* out, size_t n, const Fe* scalar, uint64_t exp,
                        cudaStream_t st);
+    // out[j] = map(first * ratio^j): mode 0 the point itself, 1 minus *cst, 2 inv_van[j mod van_len] * prod (x_j - roots[r])
+    // (all elements in Montgomery form; roots / inv_van are host arrays)
+    int (*coset_map)(Ctx&, int mode, uint4* out, size_t n, const Fe& ratio, const Fe& first, const Fe* cst, const Fe* h_roots,
+                     uint32_t num_roots, const Fe* h_inv_van, uint32_t van_len, cudaStream_t st);
     int (*batch_inversion)(Ctx&, uint4* a, size_t n, int* d_status, cudaStream_t st);
     int (*evaluate_at)(Ctx&, const uint4* a, size_t n, const Fe& g, uint4* d_out, cudaStream_t st);
     int (*selftest_mul_pre)(Ctx&, unsigned long long* d_mismatch, cudaStream_t st);

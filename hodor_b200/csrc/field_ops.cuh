@@ -572,6 +572,42 @@ struct Ops {
         return HODOR_OK;
     }
 
+    // out[j] = map(first * ratio^j), j < n (coset_map_kernel); h_roots / h_inv_van are host arrays (CM_DIVISOR), uploaded
+    // into the event-guarded workspace
+    static int coset_map(Ctx& c, int mode, uint4* out, size_t n, const Fe& ratio, const Fe& first, const Fe* cst,
+                         const Fe* h_roots, uint32_t num_roots, const Fe* h_inv_van, uint32_t van_len, cudaStream_t st) {
+        if (n == 0) return HODOR_OK;
+        maybe_evict(c);
+        uint32_t bits = 1;
+        while (((size_t)1 << bits) < n) bits++;
+        const PowTables* t = nullptr;
+        std::vector<Fe> bases{ratio};
+        int rc = get_pow_tables(c, &t, bases, bits, nullptr, st);
+        if (rc) return rc;
+        const uint4 *d_roots = nullptr, *d_van = nullptr;
+        const bool divisor = mode == CM_DIVISOR;
+        if (divisor) {
+            if (van_len == 0 || (van_len & (van_len - 1)) || h_inv_van == nullptr || (num_roots && h_roots == nullptr))
+                return fail(HODOR_ERR_INVALID_ARG, "coset_map: bad divisor tables");
+            rc = c.ws_acquire(((size_t)num_roots + van_len) * sizeof(Fe), st);
+            if (rc) return rc;
+            Fe* w = (Fe*)c.ws;
+            // pageable sources: the runtime stages them before cudaMemcpyAsync returns
+            if (num_roots) HODOR_CUDA_TRY(cudaMemcpyAsync(w, h_roots, (size_t)num_roots * sizeof(Fe), cudaMemcpyHostToDevice, st));
+            HODOR_CUDA_TRY(cudaMemcpyAsync(w + num_roots, h_inv_van, (size_t)van_len * sizeof(Fe), cudaMemcpyHostToDevice, st));
+            d_roots = (const uint4*)w;
+            d_van = (const uint4*)(w + num_roots);
+        }
+        const unsigned grid = (unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+        {
+            ProfScope ps(c, st, "coset_map");
+            coset_map_kernel<F><<<grid ? grid : 1, 256, 0, st>>>(mode, out, n, t->two_level(), first, cst ? *cst : Fld::zero(), d_roots,
+                                                               num_roots, d_van, divisor ? van_len - 1 : 0u, 0u);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return divisor ? c.ws_release(st) : HODOR_OK;
+    }
+
     static int elementwise(Ctx& c, int op, const uint4* a, const uint4* b, uint4* out, size_t n, const Fe* scalar,
                            uint64_t exp, cudaStream_t st) {
         if (op < 0 || op >= EW_NUM_OPS) return fail(HODOR_ERR_INVALID_ARG, "unknown elementwise op");
@@ -768,6 +804,7 @@ struct Ops {
         o.ntt = ntt;
         o.scale_pow = scale_pow;
         o.elementwise = elementwise;
+        o.coset_map = coset_map;
         o.batch_inversion = batch_inversion;
         o.evaluate_at = evaluate_at;
         o.selftest_mul_pre = selftest_mul_pre;

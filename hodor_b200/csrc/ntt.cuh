@@ -579,4 +579,32 @@ __global__ void elementwise_kernel(int op, const uint4* a, const uint4* b, uint4
     }
 }
 
+// Points of a coset and two maps over them (the setup work of `Prover::new`):
+//   x_j = first * ratio^j                                   src/precomputations/mod.rs:14-66 (omegas / coset / omegas_inv)
+//   CM_LINEAR   x_j - c                                     src/ali/per_register/mod.rs:214-224 (X - omega^row on the coset)
+//   CM_DIVISOR  inv_van[j & van_mask] * prod_r (x_j - roots[r])   src/ali/per_register/mod.rs:60-162: x_j^T - 1 takes only
+//               E/T distinct values on the evaluation coset, so their inverses come in as a small table
+enum : int { CM_POINTS = 0, CM_LINEAR = 1, CM_DIVISOR = 2 };
+template <class F>
+__global__ void coset_map_kernel(int mode, uint4* out, size_t n, TwoLevel pw, const __grid_constant__ Fe first,
+                                 const __grid_constant__ Fe c, const uint4* roots, uint32_t num_roots, const uint4* inv_van,
+                                 uint32_t van_mask, uint32_t zero) {
+    const uint32_t oz = threadIdx.x & zero;
+    const Field<F> fld(oz);
+    FePre fp;
+    fld.make_pre(ld_param(first, oz), fp.w, fp.q);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        Fe x = mul_by(fld, two_level_pow(fld, pw, 0, 0, j), fp);
+        if (mode == CM_LINEAR) {
+            x = fld.sub(x, ld_param(c, oz));
+        } else if (mode == CM_DIVISOR) {
+            Fe d = ld_fe(inv_van, j & van_mask);
+            for (uint32_t r = 0; r < num_roots; r++) d = fld.mul(d, fld.sub(x, ld_fe(roots, r)));
+            x = d;
+        }
+        st_fe(out, j, x);
+    }
+}
+
+
 }  // namespace hodor

@@ -33,6 +33,7 @@ import torch
 
 from . import device as dev
 from . import field as fld
+from . import precomputations as P
 from .device import DevicePolynomial as DP
 from .domains import Domain
 from .iop import BLAKE2S_KEY, BLAKE2S_PERSONAL, Blake2sLeafEncoder, CommittedOracle
@@ -117,27 +118,13 @@ class FibonacciProver:
         fid, T = field_id, self.T
         self.omega = Domain.new_for_size(fid, T).generator
         self.omega_N = Domain.new_for_size(fid, self.N).generator
-        one, gen = fld.one(fid), fld.multiplicative_generator(fid)
-        neg = lambda x: fld.sub(fid, fld.zero(), x)  # noqa: E731
-        # x_i = g * omega^i: the coset the constraints are evaluated on (coset_lde factor = max degree = 1)
-        xs = DP.filled(fid, T, gen)
-        xs.distribute_powers(None, self.omega)
+        # constraints are evaluated on the coset g * <omega> (coset_lde factor = max constraint degree = 1), so the
+        # constraints domain is the column domain; both divisor families are one C-ABI call each
+        col = Domain.new_for_size(fid, T)
         # Dense{start_at 0, span 1}: (x - omega^(T-1)) / (x^T - 1)  (:60-162)
-        d = xs.clone()
-        d.pow(None, T)
-        d.add_constant(None, neg(one))
-        d.batch_inversion(None)
-        lin = xs.clone()
-        lin.add_constant(None, neg(fld.pow_(fid, self.omega, T - 1)))
-        d.mul_assign(None, lin)
-        self.dense_div = d
+        self.dense_div, _ = P.inverse_divisor_for_dense_constraint_in_coset(col, col, P.DenseConstraint(0, 1), T)
         # boundary rows: 1 / (x - omega^row)  (:214-227)
-        self.bdiv = {}
-        for row in (0, T - 1):
-            q = xs.clone()
-            q.add_constant(None, neg(fld.pow_(fid, self.omega, row)))
-            q.batch_inversion(None)
-            self.bdiv[row] = q
+        self.bdiv = {row: P.boundary_constraint_inverse_divisor(col, col, row) for row in (0, T - 1)}
         torch.cuda.synchronize()
 
     def prove(self, a_col: np.ndarray, b_col: np.ndarray, keep_stages: bool = False) -> FibProof:

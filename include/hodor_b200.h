@@ -228,6 +228,28 @@ int hodor_cuda_merkle_top_dev(void* d_nodes, uint64_t w, void* d_root, void* d_c
 /* one FRI layer: d_out[idx], idx < n/2, from d_in (n values); challenge read from d_challenge */
 int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domain_size, uint32_t layer,
                             const void* d_challenge, void* d_out, int field_id, void* stream);
+/* PrecomputedOmegas::new_for_domain (src/precomputations/mod.rs:14-66) as device vectors: d_omegas[i] = omega^i and
+ * d_coset[i] = g * omega^i (n = 2^log_n elements each), d_omegas_inv[i] = omega^-i (n/2 elements); omega the generator of
+ * the size-n domain, g the field's multiplicative generator.  Any pointer may be NULL to skip that vector. */
+int hodor_cuda_precomputed_omegas_dev(void* d_omegas, void* d_coset, void* d_omegas_inv, uint32_t log_n, int field_id,
+                                      void* stream);
+/* inverse_divisor_for_dense_constraint_in_coset (src/ali/per_register/mod.rs:60-162): for x_j = g * w_E^j over the
+ * evaluation domain of size E = 2^log_evaluation, d_out[j] = prod_root (x_j - root) / (x_j^T - 1), T = 2^log_column the
+ * column domain, roots = w_T^k for k in [0, start_at) and [num_rows - span, T).  *divisor_degree (may be NULL) gets
+ * T - start_at - (T - num_rows) - span (:71-75). */
+int hodor_cuda_ali_dense_inverse_divisor_dev(void* d_out, uint32_t log_column, uint32_t log_evaluation, uint64_t start_at,
+                                             uint64_t span, uint64_t num_rows, uint64_t* divisor_degree, int field_id,
+                                             void* stream);
+/* boundary-constraint divisor (src/ali/per_register/mod.rs:214-227): d_out[j] = 1 / (x_j - w_T^row) on the same coset;
+ * returns after the batch inversion has completed (HODOR_ERR_NOT_INVERTIBLE if a point hits the root). */
+int hodor_cuda_ali_boundary_inverse_divisor_dev(void* d_out, uint32_t log_column, uint32_t log_evaluation, uint64_t row,
+                                                int field_id, void* stream);
+/* The same three with host output vectors (a Rust Vec<F>); any vector of precomputed_omegas may be NULL. */
+int hodor_cuda_precomputed_omegas(uint64_t* omegas, uint64_t* coset, uint64_t* omegas_inv, uint32_t log_n, int field_id);
+int hodor_cuda_ali_dense_inverse_divisor(uint64_t* out, uint32_t log_column, uint32_t log_evaluation, uint64_t start_at,
+                                         uint64_t span, uint64_t num_rows, uint64_t* divisor_degree, int field_id);
+int hodor_cuda_ali_boundary_inverse_divisor(uint64_t* out, uint32_t log_column, uint32_t log_evaluation, uint64_t row,
+                                            int field_id);
 /* distribute_powers (src/fft/mod.rs:110-123) in place on a device vector: a[j] <- a[j] * g^j */
 int hodor_cuda_distribute_powers_dev(void* d_a, uint64_t n, const uint64_t g[4], int field_id, void* stream);
 int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, int field_id,

@@ -289,6 +289,48 @@ std::vector<Polynomial<F, Values>> lde_batch(const std::vector<Polynomial<F, Coe
     return result;
 }
 
+// ---- setup of Prover::new ----------------------------------------------------------------------
+// src/precomputations/mod.rs:7-66
+template <class F>
+struct PrecomputedOmegas {
+    std::vector<F> omegas, coset, omegas_inv;
+    static PrecomputedOmegas new_for_domain(const Domain<F>& domain, const Worker&) {
+        PrecomputedOmegas p;
+        p.omegas.resize(domain.size);
+        p.coset.resize(domain.size);
+        p.omegas_inv.resize(domain.size / 2);
+        check(hodor_cuda_precomputed_omegas(reinterpret_cast<uint64_t*>(p.omegas.data()), reinterpret_cast<uint64_t*>(p.coset.data()),
+                                            domain.size >= 2 ? reinterpret_cast<uint64_t*>(p.omegas_inv.data()) : nullptr,
+                                            (uint32_t)domain.power_of_two, F::ID));
+        return p;
+    }
+};
+struct DenseConstraint {  // src/air/mod.rs:30-33
+    size_t start_at = 0, span = 1;
+};
+// src/ali/per_register/mod.rs:60-162 -> (inverse divisor over g * <evaluation domain>, divisor degree)
+template <class F>
+std::pair<Polynomial<F, Values>, size_t> inverse_divisor_for_dense_constraint_in_coset(const Domain<F>& column_domain,
+                                                                                       const Domain<F>& evaluation_domain,
+                                                                                       DenseConstraint dense_constraint,
+                                                                                       uint64_t num_rows, const Worker&) {
+    std::vector<F> out(evaluation_domain.size);
+    uint64_t degree = 0;
+    check(hodor_cuda_ali_dense_inverse_divisor(reinterpret_cast<uint64_t*>(out.data()), (uint32_t)column_domain.power_of_two,
+                                               (uint32_t)evaluation_domain.power_of_two, dense_constraint.start_at,
+                                               dense_constraint.span, num_rows, &degree, F::ID));
+    return {Polynomial<F, Values>::from_values(std::move(out)), (size_t)degree};
+}
+// src/ali/per_register/mod.rs:214-227: 1 / (X - omega^row) over the coset of the constraints domain
+template <class F>
+Polynomial<F, Values> boundary_constraint_inverse_divisor(const Domain<F>& column_domain, const Domain<F>& constraints_domain,
+                                                          uint64_t row, const Worker&) {
+    std::vector<F> out(constraints_domain.size);
+    check(hodor_cuda_ali_boundary_inverse_divisor(reinterpret_cast<uint64_t*>(out.data()), (uint32_t)column_domain.power_of_two,
+                                                  (uint32_t)constraints_domain.power_of_two, row, F::ID));
+    return Polynomial<F, Values>::from_values(std::move(out));
+}
+
 // ---- IOP -------------------------------------------------------------------------------------
 template <class F>
 struct Blake2sTreeHasher {  // src/iop/blake2s_trivial_iop.rs:63-105

@@ -343,6 +343,72 @@ def fri_commit_through_coefficients(F: Field, lde_values: Sequence[int], lde_fac
 
 
 # --------------------------------------------------------------------------------------------
+# Setup work of Prover::new: PrecomputedOmegas (src/precomputations/mod.rs:14-66) and the ALI inverse
+# divisors (src/ali/per_register/mod.rs:60-162 dense constraints, :214-227 boundary rows)
+# --------------------------------------------------------------------------------------------
+def precomputed_omegas(F: Field, log_n: int):
+    """-> (omegas[n], coset[n], omegas_inv[n/2])   (:14-66)"""
+    n, p = 1 << log_n, F.p
+    omega = F.domain_generator(log_n)
+    omega_inv = pow(omega, -1, p)
+    omegas, u = [], 1
+    for _ in range(n):  # :27-37
+        omegas.append(u)
+        u = u * omega % p
+    omegas_inv, u = [], 1
+    for _ in range(n // 2):  # :39-49
+        omegas_inv.append(u)
+        u = u * omega_inv % p
+    coset = [v * F.generator % p for v in omegas]  # :51-59
+    return omegas, coset, omegas_inv
+
+
+def inverse_divisor_for_dense_constraint_in_coset(F: Field, log_column: int, log_evaluation: int, start_at: int, span: int,
+                                                  num_rows: int):
+    """(:60-162) -> (values over g * <evaluation domain>, divisor_degree)."""
+    p = F.p
+    T, E = 1 << log_column, 1 << log_evaluation
+    divisor_degree = T - start_at - (T - num_rows) - span  # :69-75
+    w_col, w_eval = F.domain_generator(log_column), F.domain_generator(log_evaluation)
+    roots, root = [], 1
+    for _ in range(start_at):  # :81-84
+        roots.append(root)
+        root = root * w_col % p
+    last_step = num_rows - span  # :86-91
+    root = pow(w_col, last_step, p)
+    for _ in range(last_step, T):
+        roots.append(root)
+        root = root * w_col % p
+    out, x = [], F.generator  # :116-129: x = g * w_eval^i, v = x^T - 1
+    for _ in range(E):
+        out.append((pow(x, T, p) - 1) % p)
+        x = x * w_eval % p
+    if any(v == 0 for v in out):
+        raise ZeroDivisionError("batch_inversion of a vector with a zero")
+    out = [pow(v, -1, p) for v in out]  # :133 batch_inversion
+    x = F.generator
+    for i in range(E):  # :137-158
+        d = out[i]
+        for r in roots:
+            d = d * ((x - r) % p) % p
+        out[i] = d
+        x = x * w_eval % p
+    return out, divisor_degree
+
+
+def boundary_constraint_inverse_divisor(F: Field, log_column: int, log_evaluation: int, row: int) -> List[int]:
+    """(:214-227): q(X) = X - omega^row evaluated on the coset (coset_evaluate_at_domain_for_degree_one), inverted."""
+    p = F.p
+    w_col, w_eval = F.domain_generator(log_column), F.domain_generator(log_evaluation)
+    root = pow(w_col, row, p)
+    out, x = [], F.generator
+    for _ in range(1 << log_evaluation):
+        out.append((x - root) % p)
+        x = x * w_eval % p
+    return [pow(v, -1, p) for v in out]
+
+
+# --------------------------------------------------------------------------------------------
 # Test-input generator shared by the oracle, the tests and bench.py (SURVEY.md 8d):
 # SplitMix64 stream, 4 limbs per element (limb 0 first), top limb masked to NUM_BITS, rejection
 # sampled, and the accepted limbs are used DIRECTLY as the Montgomery representation.

@@ -57,6 +57,32 @@ extern "C" {
     pub fn hodor_cuda_batch_inversion(a: *mut u64, n: u64, field_id: c_int) -> c_int;
     pub fn hodor_cuda_evaluate_at(coeffs: *const u64, n: u64, g: *const u64, out: *mut u64, field_id: c_int) -> c_int;
 
+    // setup of Prover::new: src/precomputations/mod.rs:14-66, src/ali/per_register/mod.rs:60-162, 214-227
+    pub fn hodor_cuda_precomputed_omegas(
+        omegas: *mut u64,
+        coset: *mut u64,
+        omegas_inv: *mut u64,
+        log_n: u32,
+        field_id: c_int,
+    ) -> c_int;
+    pub fn hodor_cuda_ali_dense_inverse_divisor(
+        out: *mut u64,
+        log_column: u32,
+        log_evaluation: u32,
+        start_at: u64,
+        span: u64,
+        num_rows: u64,
+        divisor_degree: *mut u64,
+        field_id: c_int,
+    ) -> c_int;
+    pub fn hodor_cuda_ali_boundary_inverse_divisor(
+        out: *mut u64,
+        log_column: u32,
+        log_evaluation: u32,
+        row: u64,
+        field_id: c_int,
+    ) -> c_int;
+
     // seam 2: src/iop/mod.rs:58-92
     pub fn hodor_cuda_merkle_build(leaves: *const u64, n: u64, nodes: *mut u8, field_id: c_int) -> c_int;
     pub fn hodor_root_to_challenge(root: *const u8, out: *mut u64, field_id: c_int) -> c_int;

@@ -4,7 +4,8 @@
 //!                     `Polynomial`-level overrides in `poly.rs` (all L cosets of an LDE in one call);
 //!   * oracle       -- `CudaBlake2sIOP<F>: IOP<F>` in `iop.rs` (tree built on the GPU, `nodes` in the
 //!                     reference's heap layout) and `CommittedOracle<F>` (values + tree stay in HBM);
-//!   * FRI          -- `CudaFriIop<F>: FriIop<F>` in `fri.rs` (whole commit chain on the device).
+//!   * FRI          -- `CudaFriIop<F>: FriIop<F>` in `fri.rs` (whole commit chain on the device);
+//!   * setup        -- `PrecomputedOmegas` and the ALI inverse divisors of `Prover::new` in `ali.rs`.
 //!
 //! `Prover<F, T, I, P, PR, FRI, A>` (src/prover/mod.rs:29) takes `I` and `FRI` as type parameters, so
 //!
@@ -15,6 +16,7 @@
 //! ```
 //!
 //! plugs the GPU path in with no change to the prover.
+pub mod ali;
 pub mod ffi;
 pub mod fri;
 pub mod iop;

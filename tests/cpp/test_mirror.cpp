@@ -275,6 +275,57 @@ static void test_domain() {
     CHECK(g.pow(16) == F::one() && g.pow(8) != F::one());
 }
 
+// `Prover::new`'s setup vectors against the reference's formulas restated with scalar host arithmetic
+// (src/precomputations/mod.rs:14-66, src/ali/per_register/mod.rs:60-162, 214-227)
+template <class F>
+static void test_precomputations() {
+    const Worker worker;
+    const auto col = Domain<F>::new_for_size(16), ev = Domain<F>::new_for_size(64);
+    const auto pre = PrecomputedOmegas<F>::new_for_domain(ev, worker);
+    CHECK(pre.omegas.size() == 64 && pre.coset.size() == 64 && pre.omegas_inv.size() == 32);
+    F u = F::one();
+    for (size_t i = 0; i < 64; i++) {
+        F c = u;
+        c.mul_assign(F::multiplicative_generator());
+        CHECK(pre.omegas[i] == u && pre.coset[i] == c);
+        if (i < 32) {
+            F prod = pre.omegas_inv[i];
+            prod.mul_assign(u);
+            CHECK(prod == F::one());
+        }
+        u.mul_assign(ev.generator);
+    }
+    const size_t start_at = 2, span = 3;
+    const uint64_t num_rows = 15;
+    auto [inv, degree] = inverse_divisor_for_dense_constraint_in_coset(col, ev, DenseConstraint{start_at, span}, num_rows, worker);
+    CHECK(degree == 16 - start_at - (16 - num_rows) - span);
+    const auto boundary = boundary_constraint_inverse_divisor(col, ev, 5, worker);
+    F x = F::multiplicative_generator();
+    for (size_t j = 0; j < 64; j++) {
+        F den = x.pow(16);
+        den.sub_assign(F::one());
+        F want = den.inverse().second;
+        for (uint64_t k = 0; k < 16; k++) {
+            if (k >= start_at && k < num_rows - span) continue;
+            F t = x;
+            t.sub_assign(col.generator.pow(k));
+            want.mul_assign(t);
+        }
+        CHECK(inv.as_ref()[j] == want);
+        F b = x;
+        b.sub_assign(col.generator.pow(5));
+        CHECK(boundary.as_ref()[j] == b.inverse().second);
+        x.mul_assign(ev.generator);
+    }
+    bool threw = false;
+    try {
+        inverse_divisor_for_dense_constraint_in_coset(ev, col, DenseConstraint{0, 1}, 64, worker);
+    } catch (const std::exception&) {
+        threw = true;
+    }
+    CHECK(threw);
+}
+
 template <class F>
 static void run_all(const char* name) {
     const int before = failures;
@@ -285,6 +336,7 @@ static void run_all(const char* name) {
     test_small_iop<F>();
     test_one_fri_step<F>();
     test_committed_oracle<F>();
+    test_precomputations<F>();
     std::printf("%s: %s\n", name, failures == before ? "ok" : "FAILED");
 }
 

@@ -66,6 +66,44 @@ def check_ntt(log_n, fid=0, reps=3):
             "ms_all_reps": times}
 
 
+def ntt_phases(log_n, fid=0):
+    """Per-rank kernel times of one sharded NTT (the library's own per-launch events) beside the whole call: what is
+    left over is the two barrier collectives and waiting for the slowest peer.  No data check (check_ntt does that)."""
+    import ctypes as C
+
+    import hodor_b200 as H
+    from hodor_b200 import multigpu as mg
+    from hodor_b200._ffi import lib
+
+    rank, world = mg.comm_init()
+    m = (1 << log_n) // world
+    omega = H.Domain.new_for_size(fid, 1 << log_n).generator
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    local = torch.randint(0, 1 << 62, (m, 4), dtype=torch.int64, device="cuda", generator=g)
+    out = torch.empty_like(local)
+    for _ in range(2):
+        mg.ntt_sharded(local, log_n, omega, fid, out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.hodor_cuda_profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mg.ntt_sharded(local, log_n, omega, fid, out)
+    e1.record()
+    torch.cuda.synchronize()
+    buf = C.create_string_buffer(1 << 16)
+    lib.hodor_cuda_profile_end(buf, len(buf))
+    mine = {"rank": rank, "call_ms": e0.elapsed_time(e1), "kernels": json.loads(buf.value.decode())}
+    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+    else:
+        allr = [mine]
+    return {"check": "phases of one sharded NTT (per rank)", "ok": True, "n_gpus": world, "log_n": log_n, "ranks": allr}
+
+
 def check_lde_fri(log_n, log_f, fid=0, reps=3):
     from hodor_b200 import device as dev
     from hodor_b200 import multigpu as mg
@@ -114,7 +152,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H.init(local_rank)
-    results = [check_ntt(ntt_log_n), check_ntt(16), check_lde_fri(log_n, log_f), check_lde_fri(14, 4)]
+    if os.environ.get("HODOR_CHECK_PHASES"):  # e.g. "28,26": only the per-phase timing of the sharded NTT
+        results = [ntt_phases(int(ln)) for ln in os.environ["HODOR_CHECK_PHASES"].split(",")]
+    else:
+        results = [check_ntt(ntt_log_n), check_ntt(16), check_lde_fri(log_n, log_f), check_lde_fri(14, 4)]
     ok = all(r["ok"] for r in results)
     if rank == 0:
         for r in results:
