@@ -481,7 +481,12 @@ struct Ops {
         for (int k = 0; k < 7; k++) p.wr[k] = tw->wr[k];
         if (c.peer_store.on) {  // set by hodor_cuda_ntt_sharded around step A (sharded.cu)
             if (log_l != 0) return fail(HODOR_ERR_INVALID_ARG, "internal: peer stores with cosets");
-            p.peer_on = 1;
+            // 2: no fence inside the kernel.  The kernel boundary orders the stores before the barrier collective that
+            // follows on this stream, and that collective's own system-scope release / acquire (cumulative) orders
+            // them before every peer's step B.  1 (HODOR_PEER_FENCE=1): every thread additionally fences at system
+            // scope before it exits -- measured +1.1 ms on the 6.9 ms last pass of 2^28 over 2 GPUs, same result bits.
+            static const bool fence = getenv("HODOR_PEER_FENCE") && atoi(getenv("HODOR_PEER_FENCE")) == 1;
+            p.peer_on = fence ? 1 : 2;
             p.peer_chunk_log = c.peer_store.chunk_log;
             p.peer_rank = c.peer_store.rank;
             for (int k = 0; k < 16; k++) p.peer[k] = c.peer_store.base[k];

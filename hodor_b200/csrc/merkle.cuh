@@ -222,6 +222,23 @@ DEV void st_digest(uint4* base, size_t idx, const Digest& d) {
     base[2 * idx] = make_uint4(d.w[0], d.w[1], d.w[2], d.w[3]);
     base[2 * idx + 1] = make_uint4(d.w[4], d.w[5], d.w[6], d.w[7]);
 }
+// the same for arrays known to live in HBM: one 256-bit access per digest / leaf (ntt.cuh, HODOR_LDST256)
+DEV Digest ldg_digest(const uint4* base, size_t idx) {
+#if HODOR_LDST256
+    Digest d;
+    ld256(base + 2 * idx, d.w);
+    return d;
+#else
+    return ld_digest(base, idx);
+#endif
+}
+DEV void stg_digest(uint4* base, size_t idx, const Digest& d) {
+#if HODOR_LDST256
+    st256(base + 2 * idx, d.w);
+#else
+    st_digest(base, idx, d);
+#endif
+}
 
 // Where leaf b of a tree lives.  Default: in[b].  Interleaved (a layer that arrived as G chunks of `chunk`
 // elements, chunk r holding the cyclic slice v[r + G*t] of the natural-order vector -- the receive side of
@@ -241,13 +258,13 @@ DEV size_t leaf_index(const LeafMap& m, size_t b) {
 template <int K, bool LEAF>
 DEV Digest merkle_subtree(const B2sState& key, const uint4* in, uint4* nodes, size_t w_in, size_t first, const LeafMap& lm) {
     if constexpr (K == 0) {
-        if constexpr (LEAF) return tree_hash_leaf(key, ld_digest(in, leaf_index(lm, first)));
-        else return ld_digest(in, leaf_index(lm, first));  // a node level may arrive as cyclic chunks as well
+        if constexpr (LEAF) return tree_hash_leaf(key, ldg_digest(in, leaf_index(lm, first)));
+        else return ldg_digest(in, leaf_index(lm, first));  // a node level may arrive as cyclic chunks as well
     } else {
         const Digest l = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first, lm);
         const Digest r = merkle_subtree<K - 1, LEAF>(key, in, nodes, w_in, first + ((size_t)1 << (K - 1)), lm);
         const Digest d = tree_hash_node(key, l, r);
-        st_digest(nodes, (w_in >> K) + (first >> K), d);
+        stg_digest(nodes, (w_in >> K) + (first >> K), d);
         return d;
     }
 }
@@ -262,7 +279,7 @@ DEV Digest merkle_subtree_fn(const B2sState& key, uint4* nodes, size_t w_in, siz
         const Digest l = merkle_subtree_fn<K - 1>(key, nodes, w_in, first, leaf_hash);
         const Digest r = merkle_subtree_fn<K - 1>(key, nodes, w_in, first + ((size_t)1 << (K - 1)), leaf_hash);
         const Digest d = tree_hash_node(key, l, r);
-        st_digest(nodes, (w_in >> K) + (first >> K), d);
+        stg_digest(nodes, (w_in >> K) + (first >> K), d);
         return d;
     }
 }
@@ -271,7 +288,7 @@ DEV Digest merkle_subtree_fn(const B2sState& key, uint4* nodes, size_t w_in, siz
 template <int K>
 DEV Digest merkle_block_root(const B2sState& key, const uint4* in, size_t first) {
     if constexpr (K == 0) {
-        return tree_hash_leaf(key, ld_digest(in, first));
+        return tree_hash_leaf(key, ldg_digest(in, first));
     } else {
         const Digest l = merkle_block_root<K - 1>(key, in, first);
         const Digest r = merkle_block_root<K - 1>(key, in, first + ((size_t)1 << (K - 1)));
@@ -284,7 +301,7 @@ template <int K>
 __global__ void __launch_bounds__(256) merkle_block_roots_kernel(const uint4* in, uint4* out, size_t blocks,
                                                                  const __grid_constant__ B2sState key) {
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < blocks; g += (size_t)gridDim.x * blockDim.x)
-        st_digest(out, g, merkle_block_root<K>(key, in, g << K));
+        stg_digest(out, g, merkle_block_root<K>(key, in, g << K));
 }
 
 // grid-stride over groups of 2^K inputs; writes K node levels

@@ -75,35 +75,82 @@ struct NttPass {
     FePre wr[7];        // omega_16^k, k = 1..7  (omega_8 = wr[1], omega_4 = wr[3])
 };
 
+// One element = 32 bytes = one sector.  sm_100 has 256-bit global loads / stores (LDG.E.256 / STG.E.256, PTX
+// ld/st.global.v8.b32): one full-sector access per element instead of two half-sector ones -- half the LSU
+// instructions, and a store that crosses NVLink (the peer stores of the sharded NTT) travels as whole sectors.
+// Needs 32-byte aligned element arrays (every cudaMalloc'ed / torch buffer is; rows are 32 bytes).
+#ifndef HODOR_LDST256
+#define HODOR_LDST256 1
+#endif
+DEV void ld256(const void* ptr, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(ptr));
+}
+DEV void st256(void* ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 DEV Fe ld_fe(const uint4* base, size_t idx) {
+    Fe r;
+#if HODOR_LDST256
+    ld256(base + 2 * idx, r.v);
+#else
     const uint4 a = base[2 * idx], b = base[2 * idx + 1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#endif
+    return r;
+}
+DEV void st_fe(uint4* base, size_t idx, const Fe& r) {
+#if HODOR_LDST256
+    st256(base + 2 * idx, r.v);
+#else
+    base[2 * idx] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    base[2 * idx + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+#endif
+}
+DEV FePre ld_pre(const uint4* base, size_t idx) {
+    FePre r;
+#if HODOR_LDST256
+    ld256(base + 4 * idx, r.w.v);
+    ld256(base + 4 * idx + 2, r.q.v);
+#else
+    const uint4 a = base[4 * idx], b = base[4 * idx + 1], c = base[4 * idx + 2], d = base[4 * idx + 3];
+    r.w.v[0] = a.x; r.w.v[1] = a.y; r.w.v[2] = a.z; r.w.v[3] = a.w;
+    r.w.v[4] = b.x; r.w.v[5] = b.y; r.w.v[6] = b.z; r.w.v[7] = b.w;
+    r.q.v[0] = c.x; r.q.v[1] = c.y; r.q.v[2] = c.z; r.q.v[3] = c.w;
+    r.q.v[4] = d.x; r.q.v[5] = d.y; r.q.v[6] = d.z; r.q.v[7] = d.w;
+#endif
+    return r;
+}
+DEV void st_pre(uint4* base, size_t idx, const FePre& r) {
+#if HODOR_LDST256
+    st256(base + 4 * idx, r.w.v);
+    st256(base + 4 * idx + 2, r.q.v);
+#else
+    base[4 * idx] = make_uint4(r.w.v[0], r.w.v[1], r.w.v[2], r.w.v[3]);
+    base[4 * idx + 1] = make_uint4(r.w.v[4], r.w.v[5], r.w.v[6], r.w.v[7]);
+    base[4 * idx + 2] = make_uint4(r.q.v[0], r.q.v[1], r.q.v[2], r.q.v[3]);
+    base[4 * idx + 3] = make_uint4(r.q.v[4], r.q.v[5], r.q.v[6], r.q.v[7]);
+#endif
+}
+template <class F>
+DEV Fe mul_by(const Field<F>& fld, const Fe& a, const FePre& m) {
+    return fld.mul_pre(a, m.w, m.q);
+}
+// element idx of a shared-memory array of contiguous 32-byte elements (ld_fe / st_fe are global-only)
+DEV Fe lds_elem(const uint4* sm, size_t idx) {
+    const uint4 a = sm[2 * idx], b = sm[2 * idx + 1];
     Fe r;
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
     r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
     return r;
 }
-DEV void st_fe(uint4* base, size_t idx, const Fe& r) {
-    base[2 * idx] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    base[2 * idx + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
-}
-DEV FePre ld_pre(const uint4* base, size_t idx) {
-    const uint4 a = base[4 * idx], b = base[4 * idx + 1], c = base[4 * idx + 2], d = base[4 * idx + 3];
-    FePre r;
-    r.w.v[0] = a.x; r.w.v[1] = a.y; r.w.v[2] = a.z; r.w.v[3] = a.w;
-    r.w.v[4] = b.x; r.w.v[5] = b.y; r.w.v[6] = b.z; r.w.v[7] = b.w;
-    r.q.v[0] = c.x; r.q.v[1] = c.y; r.q.v[2] = c.z; r.q.v[3] = c.w;
-    r.q.v[4] = d.x; r.q.v[5] = d.y; r.q.v[6] = d.z; r.q.v[7] = d.w;
-    return r;
-}
-DEV void st_pre(uint4* base, size_t idx, const FePre& r) {
-    base[4 * idx] = make_uint4(r.w.v[0], r.w.v[1], r.w.v[2], r.w.v[3]);
-    base[4 * idx + 1] = make_uint4(r.w.v[4], r.w.v[5], r.w.v[6], r.w.v[7]);
-    base[4 * idx + 2] = make_uint4(r.q.v[0], r.q.v[1], r.q.v[2], r.q.v[3]);
-    base[4 * idx + 3] = make_uint4(r.q.v[4], r.q.v[5], r.q.v[6], r.q.v[7]);
-}
-template <class F>
-DEV Fe mul_by(const Field<F>& fld, const Fe& a, const FePre& m) {
-    return fld.mul_pre(a, m.w, m.q);
+DEV void sts_elem(uint4* sm, size_t idx, const Fe& r) {
+    sm[2 * idx] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    sm[2 * idx + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 // shared-memory tile: two planes of uint4 so that a quarter warp touching 8 adjacent columns
 // reads 128 contiguous bytes
@@ -439,7 +486,7 @@ __global__ void __launch_bounds__(PassOccupancy<B>::THREADS, PassOccupancy<B>::M
         ntt_group<F, B, R4, 0, R1 + R2 + R3, false, false, true>(fld, p, sm, tid, oz, load_global, store_global);
     }
     if constexpr (LAST) {
-        if (p.peer_on) __threadfence_system();  // peer stores are performed before the kernel counts as complete
+        if (p.peer_on == 1) __threadfence_system();  // optional (HODOR_PEER_FENCE=1), see Ops::ntt
     }
 }
 
@@ -469,24 +516,24 @@ __global__ void __launch_bounds__(1024) ntt_small_kernel(const __grid_constant__
         if (p.coset.lo != nullptr)
             v = fld.mul(v, two_level_pow(fld, p.coset, (size_t)coset * p.coset_stride_lo,
                                          (size_t)coset * p.coset_stride_hi, j));
-        st_fe(sm, j, v);
+        sts_elem(sm, j, v);
     }
     __syncthreads();
     for (uint32_t st = 0; st < ln; st++) {
         const uint32_t half = n >> (st + 1);
         for (uint32_t q = tid; q < n / 2; q += nt) {
             const uint32_t i = q & (half - 1u), blk = (q / half) * 2 * half;
-            const Fe u = ld_fe(sm, blk + i), v = ld_fe(sm, blk + i + half);
-            st_fe(sm, blk + i, fld.add(u, v));
+            const Fe u = lds_elem(sm, blk + i), v = lds_elem(sm, blk + i + half);
+            sts_elem(sm, blk + i, fld.add(u, v));
             Fe d = fld.sub(u, v);
             if (i != 0) d = fld.mul(d, ld_fe(p.tw, (size_t)i << st));
-            st_fe(sm, blk + i + half, d);
+            sts_elem(sm, blk + i + half, d);
         }
         __syncthreads();
     }
     for (uint32_t j = tid; j < n; j += nt) {
         const uint32_t k = ln ? (__brev(j) >> (32 - ln)) : 0u;
-        Fe v = ld_fe(sm, j);
+        Fe v = lds_elem(sm, j);
         if (p.flags & PASS_OUT_CONST) v = fld.mul(v, ld_param(p.out_const, oz));
         if (p.flags & PASS_OUT_POW) v = fld.mul(v, two_level_pow(fld, p.out_pow, 0, 0, k));
         st_fe(p.out, (size_t)coset + ((size_t)k << p.log_l), v);

@@ -106,13 +106,13 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint4* a, size_
         for (uint32_t k = kmax; k >= 1; k--) acc = fld.add(mul_by(fld, acc, y), ld_fe(a, t + M * (k - 1)));
         acc = fld.mul(acc, fld.pow(ld_param(g, oz), (uint64_t)t));
     }
-    st_fe(sm, threadIdx.x, acc);
+    sts_elem(sm, threadIdx.x, acc);
     __syncthreads();
     for (uint32_t h = 128; h >= 1; h >>= 1) {
-        if (threadIdx.x < h) st_fe(sm, threadIdx.x, fld.add(ld_fe(sm, threadIdx.x), ld_fe(sm, threadIdx.x + h)));
+        if (threadIdx.x < h) sts_elem(sm, threadIdx.x, fld.add(lds_elem(sm, threadIdx.x), lds_elem(sm, threadIdx.x + h)));
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_fe(partial, blockIdx.x, ld_fe(sm, 0));
+    if (threadIdx.x == 0) st_fe(partial, blockIdx.x, lds_elem(sm, 0));
 }
 
 template <class F>
@@ -121,13 +121,13 @@ __global__ void __launch_bounds__(256) eval_final_kernel(const uint4* partial, s
     const Field<F> fld(threadIdx.x & zero);
     Fe acc = Field<F>::zero();
     for (size_t i = threadIdx.x; i < count; i += 256) acc = fld.add(acc, ld_fe(partial, i));
-    st_fe(sm, threadIdx.x, acc);
+    sts_elem(sm, threadIdx.x, acc);
     __syncthreads();
     for (uint32_t h = 128; h >= 1; h >>= 1) {
-        if (threadIdx.x < h) st_fe(sm, threadIdx.x, fld.add(ld_fe(sm, threadIdx.x), ld_fe(sm, threadIdx.x + h)));
+        if (threadIdx.x < h) sts_elem(sm, threadIdx.x, fld.add(lds_elem(sm, threadIdx.x), lds_elem(sm, threadIdx.x + h)));
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_fe(out, 0, ld_fe(sm, 0));
+    if (threadIdx.x == 0) st_fe(out, 0, lds_elem(sm, 0));
 }
 
 // Self-test of Field::mul_pre: a chain of multiplications through the Montgomery multiplier, through

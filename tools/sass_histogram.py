@@ -40,7 +40,7 @@ def main():
                 funcs[cur].append(m.group(2))
     print(f"# SASS opcode histograms (`cuobjdump -sass {os.path.relpath(LIB, ROOT)}`, sm_100a)\n")
     print("Made by `tools/sass_histogram.py`.  16 bytes per instruction.  No `UTMALDG` / `UBLKCP` (TMA) and no `SHFL` appear: the tiles are "
-          "staged by per-thread 128-bit `LDG.E.128` / `STS.128` because each thread multiplies its own elements by its own streamed table "
+          "staged by per-thread 256-bit global accesses (`LDG.E.256` / `STG.E.256`, one 32-byte element = one sector per instruction, sm_100 only) and `STS.128` / `LDS.128` because each thread multiplies its own elements by its own streamed table "
           "entries (nothing to broadcast or bulk-copy into a shared tile that fits: a 2^8 x 8 tile's table entries are 128 KiB), and the "
           "exchange between butterfly groups goes through shared memory, not shuffles (a warp-autonomous shuffle variant was measured "
           "in round 1: -13 %).  See profiles/r02_experiments.md.\n")
