@@ -555,23 +555,27 @@ int hodor_cuda_stream_synchronize(void* stream) {
 int hodor_cuda_ntt_dev(const void* d_in, void* d_out, uint32_t log_n, const uint64_t omega[4], int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_out);
     return ops->ntt(*c, (const uint4*)d_in, (uint4*)d_out, log_n, 0, fe_from_u64(omega), nullptr, nullptr, 0, nullptr,
                     pick_stream(c, stream));
 }
 int hodor_cuda_fft_dev(const void* d_in, void* d_out, uint32_t log_n, int coset, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_out);
     return do_fft(*c, ops, (const uint4*)d_in, (uint4*)d_out, log_n, coset, pick_stream(c, stream));
 }
 int hodor_cuda_ifft_dev(const void* d_in, void* d_out, uint32_t log_n, int coset, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_out);
     return do_ifft(*c, ops, (const uint4*)d_in, (uint4*)d_out, log_n, coset, pick_stream(c, stream));
 }
 int hodor_cuda_lde_dev(const void* d_coeffs, uint32_t log_n, uint32_t log_factor, int coset, void* d_out, int field_id,
                        void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_coeffs, d_out);
     if (d_coeffs == d_out && log_factor) return fail(HODOR_ERR_INVALID_ARG, "lde: input and output must not alias");
     return do_lde(*c, ops, (const uint4*)d_coeffs, (uint4*)d_out, log_n, log_factor, coset, pick_stream(c, stream));
 }
@@ -579,6 +583,7 @@ int hodor_cuda_merkle_build_dev(const void* d_leaves, uint64_t n, void* d_nodes,
                                 int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_leaves, d_nodes, d_root, d_challenge);
     return do_merkle(*c, ops, (const uint4*)d_leaves, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,
                      pick_stream(c, stream));
 }
@@ -586,6 +591,7 @@ int hodor_cuda_merkle_build_shard_dev(const void* d_chunks, uint64_t n, uint32_t
                                       void* d_challenge, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_chunks, d_nodes, d_root);
     if (log_g > 4 || !is_pow2(n) || (n >> log_g) <= 1024)
         return fail(HODOR_ERR_INVALID_ARG, "merkle_build_shard: need log_g <= 4 and more than 1024 leaves per chunk");
     return do_merkle(*c, ops, (const uint4*)d_chunks, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,
@@ -594,6 +600,7 @@ int hodor_cuda_merkle_build_shard_dev(const void* d_chunks, uint64_t n, uint32_t
 int hodor_cuda_merkle_top_dev(void* d_nodes, uint64_t w, void* d_root, void* d_challenge, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_nodes, d_root, d_challenge);
     if (!is_pow2(w) || w > 4096) return fail(HODOR_ERR_INVALID_ARG, "merkle_top: width must be a power of two <= 4096");
     return ops->merkle_tail(*c, (const uint4*)d_nodes, (uint4*)d_nodes, (uint32_t)w, false, (uint4*)d_root, (uint4*)d_challenge,
                             pick_stream(c, stream));
@@ -602,6 +609,7 @@ int hodor_cuda_fri_fold_dev(const void* d_in, uint64_t n, uint64_t initial_domai
                             const void* d_challenge, void* d_out, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_challenge, d_out);
     if (!is_pow2(n) || n < 2 || !is_pow2(initial_domain_size) || (initial_domain_size >> layer) != n)
         return fail(HODOR_ERR_INVALID_ARG, "fri_fold: n must equal initial_domain_size >> layer, both powers of two");
     return ops->fri_fold(*c, (const uint4*)d_in, n, log2u(initial_domain_size), layer, (const uint4*)d_challenge,
@@ -612,6 +620,7 @@ int hodor_cuda_fri_fold_shard_dev(const void* d_in, uint64_t n_local, uint64_t i
                                   void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_challenge, d_out);
     const uint64_t g = (uint64_t)1 << log_g;
     if (!is_pow2(n_local) || n_local < 2 || !is_pow2(initial_domain_size) || rank >= g ||
         ((initial_domain_size >> layer) >> log_g) != n_local)
@@ -623,6 +632,7 @@ int hodor_cuda_lde_cosets_dev(const void* d_coeffs, uint32_t log_n, uint32_t log
                               uint32_t coset_stride, uint32_t log_count, void* d_out, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_coeffs, d_out);
     const uint64_t L = (uint64_t)1 << log_factor, cnt = (uint64_t)1 << log_count;
     if (log_count > log_factor || coset_stride == 0 || first_coset + (cnt - 1) * coset_stride >= L)
         return fail(HODOR_ERR_INVALID_ARG, "lde_cosets: coset subset out of range");
@@ -642,6 +652,7 @@ int hodor_cuda_lde_cosets_dev(const void* d_coeffs, uint32_t log_n, uint32_t log
 int hodor_cuda_distribute_powers_dev(void* d_a, uint64_t n, const uint64_t g[4], int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_a);
     if (n == 0) return HODOR_OK;
     return ops->scale_pow(*c, (uint4*)d_a, (size_t)n, fe_from_u64(g), pick_stream(c, stream));
 }
@@ -734,6 +745,7 @@ int hodor_cuda_precomputed_omegas_dev(void* d_omegas, void* d_coset, void* d_ome
                                       void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_omegas, d_coset, d_omegas_inv);
     return precomputed_omegas_impl(c, ops, d_omegas, d_coset, d_omegas_inv, log_n, pick_stream(c, stream));
 }
 int hodor_cuda_ali_dense_inverse_divisor_dev(void* d_out, uint32_t log_column, uint32_t log_evaluation, uint64_t start_at,
@@ -741,12 +753,14 @@ int hodor_cuda_ali_dense_inverse_divisor_dev(void* d_out, uint32_t log_column, u
                                              void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_out);
     return ali_dense_impl(c, ops, d_out, log_column, log_evaluation, start_at, span, num_rows, divisor_degree, pick_stream(c, stream));
 }
 int hodor_cuda_ali_boundary_inverse_divisor_dev(void* d_out, uint32_t log_column, uint32_t log_evaluation, uint64_t row,
                                                 int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_out);
     return ali_boundary_impl(c, ops, d_out, log_column, log_evaluation, row, pick_stream(c, stream));
 }
 // host-vector forms (what a Rust caller holding Vec<F> binds): computed in the library's I/O buffer, copied out
@@ -802,6 +816,7 @@ int hodor_cuda_elementwise_dev(int op, const void* d_a, const void* d_b, void* d
                                void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_a, d_b, d_out);
     if (op < 0 || op > 3) return fail(HODOR_ERR_INVALID_ARG, "elementwise: op must be 0..3 (use hodor_cuda_poly_op_dev for the scalar forms)");
     return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, nullptr, 0, pick_stream(c, stream));
 }
@@ -809,6 +824,7 @@ int hodor_cuda_poly_op_dev(int op, const void* d_a, const void* d_b, const uint6
                            uint64_t n, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_a, d_b, d_out);
     Fe s;
     if (scalar) s = fe_from_u64(scalar);
     return ops->elementwise(*c, op, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n, scalar ? &s : nullptr, exp,
@@ -817,6 +833,7 @@ int hodor_cuda_poly_op_dev(int op, const void* d_a, const void* d_b, const uint6
 int hodor_cuda_batch_inversion_dev(void* d_a, uint64_t n, int* d_status, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_a);
     if (d_status == nullptr) return fail(HODOR_ERR_INVALID_ARG, "batch_inversion: d_status is NULL");
     return ops->batch_inversion(*c, (uint4*)d_a, (size_t)n, d_status, pick_stream(c, stream));
 }
@@ -824,12 +841,14 @@ int hodor_cuda_evaluate_at_dev(const void* d_coeffs, uint64_t n, const uint64_t 
                                void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_coeffs, d_out);
     return ops->evaluate_at(*c, (const uint4*)d_coeffs, (size_t)n, fe_from_u64(g), (uint4*)d_out, pick_stream(c, stream));
 }
 int hodor_cuda_ntt_shard_cols_dev(const void* d_in, void* d_out, uint32_t log_n, uint32_t log_g, uint32_t rank,
                                   const uint64_t omega[4], int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_out);
     if (log_g > 4 || log_n < 2 * log_g || rank >= (1u << log_g)) return fail(HODOR_ERR_INVALID_ARG, "shard_cols: bad geometry");
     // local transform of length m = n/G with root omega^G, then B_g[k] *= (omega^g)^k
     Fe w = fe_from_u64(omega), wm, wg;
@@ -842,6 +861,7 @@ int hodor_cuda_ntt_shard_rows_dev(const void* d_in, void* d_out, uint32_t log_n,
                                   const uint64_t omega[4], int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
+    CHECK_DEV_PTRS(d_in, d_out);
     return ops->shard_rows(*c, (const uint4*)d_in, (uint4*)d_out, log_n, log_g, rank, fe_from_u64(omega),
                            pick_stream(c, stream));
 }
@@ -1124,6 +1144,10 @@ hodor_tree* hodor_cuda_tree_commit(const uint64_t* values, uint64_t n, int value
         fail(HODOR_ERR_INVALID_ARG, "tree_commit: leaf count must be a power of two >= 2");
         return nullptr;
     }
+    if (values_on_device && !aligned32({values})) {
+        fail(HODOR_ERR_INVALID_ARG, "tree_commit: device element arrays must be 32-byte aligned");
+        return nullptr;
+    }
     std::unique_ptr<hodor_tree, void (*)(hodor_tree*)> t(tree_alloc(c, field_id, n, !values_on_device), tree_destroy);
     if (!t) return nullptr;
     cudaStream_t st = c->stream;
@@ -1152,6 +1176,7 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
     if (coeffs == nullptr || trees == nullptr) return fail(HODOR_ERR_INVALID_ARG, "lde_commit: NULL pointer table");
     for (uint32_t i = 0; i < count; i++) {
         if (coeffs[i] == nullptr) return fail(HODOR_ERR_INVALID_ARG, "lde_commit: NULL buffer");
+        if (coeffs_on_device) CHECK_DEV_PTRS(coeffs[i]);
         trees[i] = nullptr;
     }
     {
@@ -1385,6 +1410,10 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     const int steps = (int)log2u((n / lde_factor) / out_coeffs);
     if (steps < 1) {
         fail(HODOR_ERR_INVALID_ARG, "fri_commit: zero folding steps (the reference panics here: roots.pop() on empty)");
+        return nullptr;
+    }
+    if (lde_on_device && !aligned32({lde})) {
+        fail(HODOR_ERR_INVALID_ARG, "fri_commit: device element arrays must be 32-byte aligned");
         return nullptr;
     }
     Fe probe;

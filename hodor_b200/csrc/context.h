@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <map>
+#include <initializer_list>
 #include <mutex>
 #include <set>
 #include <string>
@@ -290,6 +291,14 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     Ctx* c = ctx();                           \
     if (!c) return HODOR_ERR_CUDA;            \
     std::lock_guard<std::mutex> _lk(c->mu)
+// element / digest arrays are read and written with 256-bit accesses (ntt.cuh ld256 / st256)
+inline bool aligned32(std::initializer_list<const void*> ps) {
+    for (const void* p : ps)
+        if (reinterpret_cast<uintptr_t>(p) & 31u) return false;
+    return true;
+}
+#define CHECK_DEV_PTRS(...) \
+    if (!aligned32({__VA_ARGS__})) return fail(HODOR_ERR_INVALID_ARG, "device element arrays must be 32-byte aligned")
 #define GET_OPS(field_id)                         \
     const FieldOps* ops = field_ops(field_id);    \
     if (!ops) return HODOR_ERR_INVALID_ARG

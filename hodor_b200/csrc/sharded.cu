@@ -309,6 +309,7 @@ int hodor_cuda_ntt_sharded(const void* d_local, void* d_out, uint32_t log_n, con
     LOCKED_CTX();
     GET_OPS(field_id);
     if (!c->comm) return fail(HODOR_ERR_INVALID_ARG, "hodor_cuda_comm_init() has not been called");
+    CHECK_DEV_PTRS(d_local, d_out);
     Comm& cm = *c->comm;
     if (log_n > 34 || log_n < 2 * cm.log_g || (cm.log_g && log_n < 4))
         return fail(HODOR_ERR_INVALID_ARG, "ntt_sharded: need 2 * log2(world) <= log_n <= 34");
@@ -374,6 +375,7 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
     LOCKED_CTX();
     GET_OPS(field_id);
     if (!c->comm) return fail(HODOR_ERR_INVALID_ARG, "hodor_cuda_comm_init() has not been called");
+    CHECK_DEV_PTRS(d_coeffs);
     Comm& cm = *c->comm;
     const uint32_t G = (uint32_t)cm.world, log_g = cm.log_g;
     if (log_g > log_factor) return fail(HODOR_ERR_INVALID_ARG, "lde_fri_sharded: more ranks than cosets");
@@ -428,7 +430,14 @@ int hodor_cuda_lde_fri_sharded(const void* d_coeffs, uint32_t log_n, uint32_t lo
     rc = ops->ntt(*c, (const uint4*)d_coeffs, val[0], log_n, blk_log ? blk_log : log_factor - log_g, omega, &shift0, &step, 0, nullptr, st);
     if (rc) return rc;
 
-    size_t gather_below = (size_t)1 << 16;
+    // Layers smaller than this are not worth two collectives each: the rest of the (strictly serial) chain is done
+    // redundantly by every rank.  HODOR_SHARD_GATHER_LOG2 overrides (sweep in profiles/r02_experiments.md).
+    const int gather_log2 = [] {
+        const char* e = getenv("HODOR_SHARD_GATHER_LOG2");
+        const int v = e ? atoi(e) : 0;
+        return v >= 12 && v <= 30 ? v : 16;
+    }();
+    size_t gather_below = (size_t)1 << gather_log2;
     if (gather_below < (size_t)4096 * B * G) gather_below = (size_t)4096 * B * G;  // the level kernels need > 1024 digests per rank
     size_t size = N;
     int layer = 0, cur = 0;

@@ -19,7 +19,8 @@
  *     HODOR_ERR_CUDA.
  *   - One process drives one GPU (hodor_cuda_init(device)).  Entry points may be called from any
  *     host thread; calls are serialised on the context.  `_dev` variants take device pointers and a
- *     cudaStream_t (as void*), enqueue work and return without synchronising.
+ *     cudaStream_t (as void*), enqueue work and return without synchronising.  Device element and digest
+ *     arrays must be 32-byte aligned (they are read with 256-bit loads): HODOR_ERR_INVALID_ARG otherwise.
  */
 #ifndef HODOR_B200_H
 #define HODOR_B200_H

@@ -895,3 +895,26 @@ def test_sharded_c_abi_two_gpus_under_torchrun():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
     assert p.returncode == 0 and len(lines) == 4 and all(l["ok"] for l in lines), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+
+
+def test_misaligned_device_pointer_is_rejected(hodor, oracle):
+    """Element arrays are read with 256-bit loads: a device pointer that is not 32-byte aligned is an argument
+    error, not a misaligned-address fault that would kill the context."""
+    import torch
+    from hodor_b200 import device as dev
+    fid, log_n = 0, 12
+    n = 1 << log_n
+    flat = torch.zeros(4 * n + 8, dtype=torch.int64, device="cuda")
+    skew = flat[2 : 2 + 4 * n].view(n, 4)  # 16 bytes past a 32-byte boundary
+    assert skew.data_ptr() % 32 == 16
+    good = dev.empty_elems(n)
+    omega = hodor.Domain.new_for_size(fid, n).generator
+    with pytest.raises(hodor.HodorError):
+        dev.ntt(skew, good, log_n, omega, fid)
+    with pytest.raises(hodor.HodorError):
+        dev.ntt(good, skew, log_n, omega, fid)
+    with pytest.raises(hodor.HodorError):
+        dev.merkle_build(skew, n, good, fid)
+    # the context is still healthy
+    a = oracle.random_elements(fid, n, seed=5)
+    assert np.array_equal(hodor.Polynomial.from_coeffs(fid, a).fft(hodor.Worker()).as_ref(), oracle.serial_fft(fid, a, omega, log_n))

@@ -104,6 +104,40 @@ def ntt_phases(log_n, fid=0):
     return {"check": "phases of one sharded NTT (per rank)", "ok": True, "n_gpus": world, "log_n": log_n, "ranks": allr}
 
 
+def lde_fri_phases(log_n, log_f, fid=0):
+    """Per-rank kernel times of one sharded LDE + FRI chain beside the whole (synchronous) call."""
+    import ctypes as C
+    import time
+
+    from hodor_b200 import device as dev
+    from hodor_b200 import multigpu as mg
+    from hodor_b200._ffi import lib
+
+    rank, world = mg.comm_init()
+    d_coeffs = dev.to_device(synthetic(1 << log_n, 77))
+    for _ in range(2):
+        mg.lde_fri_sharded(d_coeffs, log_n, log_f, True, 1, fid)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.hodor_cuda_profile_begin()
+    t0 = time.perf_counter()
+    mg.lde_fri_sharded(d_coeffs, log_n, log_f, True, 1, fid)
+    call_ms = (time.perf_counter() - t0) * 1e3
+    buf = C.create_string_buffer(1 << 16)
+    lib.hodor_cuda_profile_end(buf, len(buf))
+    kernels = json.loads(buf.value.decode())
+    mine = {"rank": rank, "call_ms": call_ms, "kernel_sum_ms": sum(k["total_ms"] for k in kernels), "kernels": kernels}
+    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+    else:
+        allr = [mine]
+    return {"check": "phases of one sharded LDE + FRI chain (per rank)", "ok": True, "n_gpus": world, "log_n": log_n,
+            "lde_factor": 1 << log_f, "ranks": allr}
+
+
 def check_lde_fri(log_n, log_f, fid=0, reps=3):
     from hodor_b200 import device as dev
     from hodor_b200 import multigpu as mg
@@ -153,7 +187,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H.init(local_rank)
     if os.environ.get("HODOR_CHECK_PHASES"):  # e.g. "28,26": only the per-phase timing of the sharded NTT
-        results = [ntt_phases(int(ln)) for ln in os.environ["HODOR_CHECK_PHASES"].split(",")]
+        results = [ntt_phases(int(ln)) for ln in os.environ["HODOR_CHECK_PHASES"].split(",") if ln]
+        for g in [x for x in os.environ.get("HODOR_CHECK_GATHER_SWEEP", "").split(",") if x]:  # "16,18,20,22"
+            os.environ["HODOR_SHARD_GATHER_LOG2"] = g
+            r = check_lde_fri(log_n, log_f)
+            r["gather_log2"] = int(g)
+            results.append(r)
+            lp = lde_fri_phases(log_n, log_f)
+            lp["gather_log2"] = int(g)
+            results.append(lp)
+        os.environ.pop("HODOR_SHARD_GATHER_LOG2", None)
+        if os.environ.get("HODOR_CHECK_PHASES_LDE"):  # "24,4"
+            a, b = (int(x) for x in os.environ["HODOR_CHECK_PHASES_LDE"].split(","))
+            results.append(lde_fri_phases(a, b))
     else:
         results = [check_ntt(ntt_log_n), check_ntt(16), check_lde_fri(log_n, log_f), check_lde_fri(14, 4)]
     ok = all(r["ok"] for r in results)
