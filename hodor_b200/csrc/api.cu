@@ -318,8 +318,16 @@ int hodor_cuda_init(int device) {
     c->device = device;
     int prio_least = 0, prio_greatest = 0;
     HODOR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-    HODOR_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
-    HODOR_CUDA_TRY(cudaStreamCreateWithPriority(&c->commit_stream, cudaStreamNonBlocking, prio_least));
+    {
+        // default: transforms at the higher priority, the hashing stream fills what they leave free
+        int p_main = prio_greatest, p_commit = prio_least;
+        if (const char* e = getenv("HODOR_COMMIT_PRIORITY")) {
+            if (!strcmp(e, "high")) { p_main = prio_least; p_commit = prio_greatest; }
+            else if (!strcmp(e, "equal")) { p_main = p_commit = prio_greatest; }
+        }
+        HODOR_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, p_main));
+        HODOR_CUDA_TRY(cudaStreamCreateWithPriority(&c->commit_stream, cudaStreamNonBlocking, p_commit));
+    }
     if (const char* e = getenv("HODOR_CONCURRENT_COMMIT")) c->concurrent_commit = atoi(e) != 0;
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     HODOR_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));

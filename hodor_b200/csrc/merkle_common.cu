@@ -25,8 +25,13 @@ static int launch_levels(Ctx& c, const uint4* in, uint4* nodes, size_t w_in, cud
         // fit into what three resident pass-kernel blocks leave free on an SM, need no shared memory, and return
         // their slot after one subtree per thread, so the block scheduler can keep the transform's blocks (higher
         // stream priority) resident and fill the gaps with hashing.
-        block = 128;
-        grid = (unsigned)((groups + block - 1) / block);
+        // HODOR_BACKFILL_PERSIST = R > 0: a persistent grid of R blocks per SM instead (grid-stride over the subtrees);
+        // with the hashing stream at the HIGHER priority (HODOR_COMMIT_PRIORITY=high) those blocks take their place as
+        // transform blocks retire and keep it, so the hashing gets a fixed share of every SM.
+        static const int persist = getenv("HODOR_BACKFILL_PERSIST") ? atoi(getenv("HODOR_BACKFILL_PERSIST")) : 0;
+        static const int bblock = getenv("HODOR_BACKFILL_BLOCK") ? atoi(getenv("HODOR_BACKFILL_BLOCK")) : 128;
+        block = (bblock == 64 || bblock == 128 || bblock == 256) ? (unsigned)bblock : 128u;
+        grid = persist > 0 ? 148u * (unsigned)persist : (unsigned)((groups + block - 1) / block);
         auto kern = merkle_levels_kernel<K, LEAF>;
         if (!c.configured_kernels.count((const void*)kern)) {  // same L1 / shared split as the pass kernels it shares SMs with
             HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

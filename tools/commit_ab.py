@@ -43,4 +43,7 @@ for _ in range(reps):
 ms = (time.perf_counter() - t0) * 1e3 / (reps * count)
 assert all(r[i].tobytes() == r0[0].tobytes() for i in range(count))
 print(json.dumps({"bench": "lde_commit_batch 2^24 x 8", "concurrent_commit": os.environ.get("HODOR_CONCURRENT_COMMIT", "1"),
+                  "commit_priority": os.environ.get("HODOR_COMMIT_PRIORITY", "low"),
+                  "backfill_persist": os.environ.get("HODOR_BACKFILL_PERSIST", "0"),
+                  "backfill_block": os.environ.get("HODOR_BACKFILL_BLOCK", "128"),
                   "ms_per_polynomial": ms, "root": r0[0].tobytes().hex()}))
