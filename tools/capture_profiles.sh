@@ -15,5 +15,5 @@ for k in lde merkle fold; do
   ncu -i gpurun_out/${TAG}_$k.ncu-rep --page details > gpurun_out/${TAG}_ncu_$k.details.txt 2>/dev/null
 done
 # launch list of a whole bench run (device times are cold-cache and serialised: compare shares, not absolutes)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-sweep --no-fib > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-sweep --no-fib --no-fields > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
 ls -la gpurun_out/ | grep ${TAG}
