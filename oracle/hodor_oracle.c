@@ -7,9 +7,14 @@
  *
  * PARITY STATUS: "parity unpinned".  The reference (@76fc894) is Rust; cargo/rustc are absent
  * from this image, so it cannot be compiled or run, and its tests contain no golden vectors for
- * this path.  The only reference-held constants, the Montgomery encodings
- * MINUS_ONE / NON_RESIDUE at src/experiments/square_root_calculator/fp2.rs:10-22, are checked
- * in tests/test_oracle_pins.py.  The un-vendored dependencies whose published algorithms are
+ * this path.  What the reference does hold is pinned: the Montgomery encodings
+ * MINUS_ONE / NON_RESIDUE (src/experiments/square_root_calculator/fp2.rs:10-22,
+ * tests/test_oracle_pins.py) and E_PRECOMPUTED / F_PRECOMPUTED (fp2.rs:51-81), the printed
+ * output of the reference's own `find_c` test: ~3000 dependent Montgomery mul / add / sub and
+ * one inversion over `experiments::Fr`, reproduced bit for bit by fe_mul / fe_add / fe_sub /
+ * fe_inv below (tests/test_reference_kat.py).  That pins row a1 (field arithmetic); the
+ * transforms, the tree and the FRI chain built on it stay unpinned.
+ * The un-vendored dependencies whose published algorithms are
  * restated here:  ff_ce "0.7" (derive(PrimeField): 4 x u64 little-endian limbs, Montgomery
  * R = 2^256, canonical representatives, ROOT_OF_UNITY = GENERATOR^((p-1)/2^S));
  * blake2s_simd "0.5" (RFC 7693 Blake2s-256 with key and personalisation).

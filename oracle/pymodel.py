@@ -11,7 +11,10 @@ compiled in this image (no cargo/rustc) and its tests hold NO golden vectors for
 (SURVEY.md section 8c).  What *is* pinned against reference-held constants:
   * Montgomery form with R = 2^256 over 4 little-endian u64 limbs:
     src/experiments/square_root_calculator/fp2.rs:10-22 (MINUS_ONE, NON_RESIDUE) -- see
-    tests/test_oracle_pins.py.
+    tests/test_oracle_pins.py;
+  * Montgomery mul / add / sub / inverse over `experiments::Fr`: E_PRECOMPUTED / F_PRECOMPUTED
+    (fp2.rs:51-81), the printed output of the reference's own `find_c` test (fp2.rs:358-412),
+    reproduced bit for bit -- tests/test_reference_kat.py.
 Everything else follows the published algorithms of the un-vendored dependencies
 (ff_ce "0.7" derive: Montgomery arithmetic, root_of_unity = g^((p-1)/2^S);
  blake2s_simd "0.5": RFC 7693 keyed+personalised Blake2s) and the reference call sites cited on
