@@ -276,6 +276,41 @@ int do_merkle(Ctx& c, const FieldOps* ops, const uint4* leaves, size_t n, uint4*
     return ops->merkle_tail(c, nodes, nodes, (uint32_t)w, false, root, chal, st);
 }
 
+// Releases everything a context owns (also the partially built one of a failed hodor_cuda_init).  Blocks still
+// held by live handles (pool_live) belong to their owners and are not touched.
+static void ctx_destroy(Ctx* c) {
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    comm_destroy(c);
+    for (auto& kv : c->pow_tables) cudaFree(kv.second.block);
+    for (auto& kv : c->ntt_tables) {
+        cudaFree(kv.second.pw.block);
+        cudaFree(kv.second.tw_b_block);
+        cudaFree(kv.second.tw_direct_block);
+    }
+    if (c->ws) cudaFree(c->ws);
+    for (int i = 0; i < 2; i++)
+        if (c->io[i]) cudaFree(c->io[i]);
+    for (auto& b : c->pool_free_list) cudaFree(b.first);
+    for (auto& kv : c->full_tables) cudaFree(kv.second.first);
+    for (auto& r : c->prof) {
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->ws_event) cudaEventDestroy(c->ws_event);
+    if (c->small) cudaFree(c->small);
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    for (int b = 0; b < 2; b++) {
+        if (c->stage[b]) cudaFreeHost(c->stage[b]);
+        if (c->stage_free[b]) cudaEventDestroy(c->stage_free[b]);
+    }
+    for (cudaStream_t st : {c->stream, c->commit_stream, c->copy_in, c->copy_out})
+        if (st) cudaStreamDestroy(st);
+    cudaGetLastError();
+    delete c;
+}
+
 }  // namespace hodor
 
 using namespace hodor;
@@ -314,7 +349,7 @@ int hodor_cuda_init(int device) {
         snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
         return fail(HODOR_ERR_CUDA, buf);
     }
-    std::unique_ptr<Ctx> c(new Ctx());
+    std::unique_ptr<Ctx, void (*)(Ctx*)> c(new Ctx(), ctx_destroy);  // an early return below releases what was created
     c->device = device;
     int prio_least = 0, prio_greatest = 0;
     HODOR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
@@ -349,37 +384,7 @@ int hodor_cuda_init(int device) {
 void hodor_cuda_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     if (!g_ctx) return;
-    cudaSetDevice(g_ctx->device);
-    cudaDeviceSynchronize();
-    comm_destroy(g_ctx);
-    for (auto& kv : g_ctx->pow_tables) cudaFree(kv.second.block);
-    for (auto& kv : g_ctx->ntt_tables) {
-        cudaFree(kv.second.pw.block);
-        cudaFree(kv.second.tw_b_block);
-        cudaFree(kv.second.tw_direct_block);
-    }
-    if (g_ctx->ws) cudaFree(g_ctx->ws);
-    for (int i = 0; i < 2; i++)
-        if (g_ctx->io[i]) cudaFree(g_ctx->io[i]);
-    for (auto& b : g_ctx->pool_free_list) cudaFree(b.first);
-    for (auto& kv : g_ctx->full_tables) cudaFree(kv.second.first);
-    for (auto& r : g_ctx->prof) {
-        cudaEventDestroy(r.start);
-        cudaEventDestroy(r.stop);
-    }
-    for (auto e : g_ctx->event_pool) cudaEventDestroy(e);
-    if (g_ctx->ws_event) cudaEventDestroy(g_ctx->ws_event);
-    cudaFree(g_ctx->small);
-    if (g_ctx->pinned_small) cudaFreeHost(g_ctx->pinned_small);
-    for (int b = 0; b < 2; b++) {
-        if (g_ctx->stage[b]) cudaFreeHost(g_ctx->stage[b]);
-        if (g_ctx->stage_free[b]) cudaEventDestroy(g_ctx->stage_free[b]);
-    }
-    cudaStreamDestroy(g_ctx->stream);
-    if (g_ctx->commit_stream) cudaStreamDestroy(g_ctx->commit_stream);
-    cudaStreamDestroy(g_ctx->copy_in);
-    cudaStreamDestroy(g_ctx->copy_out);
-    delete g_ctx;
+    ctx_destroy(g_ctx);
     g_ctx = nullptr;
 }
 
@@ -599,7 +604,7 @@ int hodor_cuda_merkle_build_shard_dev(const void* d_chunks, uint64_t n, uint32_t
                                       void* d_challenge, int field_id, void* stream) {
     LOCKED_CTX();
     GET_OPS(field_id);
-    CHECK_DEV_PTRS(d_chunks, d_nodes, d_root);
+    CHECK_DEV_PTRS(d_chunks, d_nodes, d_root, d_challenge);
     if (log_g > 4 || !is_pow2(n) || (n >> log_g) <= 1024)
         return fail(HODOR_ERR_INVALID_ARG, "merkle_build_shard: need log_g <= 4 and more than 1024 leaves per chunk");
     return do_merkle(*c, ops, (const uint4*)d_chunks, n, (uint4*)d_nodes, (uint4*)d_root, (uint4*)d_challenge,

@@ -123,6 +123,15 @@ struct Ops {
         const size_t hdr = 2 * (size_t)nb + 1;  // Fe slots: lo bases, hi bases, scale
         t.bytes = (hdr + lo_n + hi_n) * sizeof(Fe);
         HODOR_CUDA_TRY(cudaMalloc((void**)&t.block, t.bytes));
+        struct Guard {  // an early return below must not leak the block
+            PowTables& t;
+            bool keep = false;
+            ~Guard() {
+                if (keep) return;
+                cudaFree(t.block);
+                t.block = nullptr;
+            }
+        } guard{t};
         std::vector<Fe> h(hdr);
         for (uint32_t i = 0; i < nb; i++) {
             h[i] = bases[i];
@@ -148,6 +157,7 @@ struct Ops {
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         HODOR_CUDA_TRY(cudaStreamSynchronize(st));  // tables may be used from other streams later
+        guard.keep = true;
         c.table_bytes += t.bytes;
         return HODOR_OK;
     }
@@ -430,16 +440,20 @@ struct Ops {
                     t.lo_bits = log_n;
                     t.bytes = (n + 1) * sizeof(Fe);
                     HODOR_CUDA_TRY(cudaMalloc((void**)&t.block, t.bytes));
-                    HODOR_CUDA_TRY(cudaMemcpyAsync(t.block, &omega, sizeof(Fe), cudaMemcpyHostToDevice, st));
-                    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                    cudaError_t e = cudaMemcpyAsync(t.block, &omega, sizeof(Fe), cudaMemcpyHostToDevice, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
                     t.lo = t.block + 2;
-                    {
+                    if (e == cudaSuccess) {
                         ProfScope ps(c, st, "pow_table");
                         pow_table_kernel<F><<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, st>>>(
                             t.lo, (const Fe*)t.block, nullptr, (uint32_t)n, 0u);
                     }
-                    HODOR_CUDA_TRY(cudaGetLastError());
-                    HODOR_CUDA_TRY(cudaStreamSynchronize(st));
+                    if (e == cudaSuccess) e = cudaGetLastError();
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                    if (e != cudaSuccess) {
+                        cudaFree(t.block);
+                        return cuda_fail(e, "flat twiddle table");
+                    }
                     c.table_bytes += t.bytes;
                     it = c.pow_tables.emplace(key, t).first;
                 }

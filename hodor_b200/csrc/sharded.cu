@@ -322,12 +322,28 @@ int hodor_cuda_ntt_sharded(const void* d_local, void* d_out, uint32_t log_n, con
     if (cm.world == 1)  // nothing to exchange, and the G-point DFT is the identity
         return ops->ntt(*c, (const uint4*)d_local, (uint4*)d_out, log_n, 0, wm, nullptr, nullptr, 0, nullptr, st);
     const size_t had = cm.buf_bytes[1];
+    // The receive buffer grows (the same decision on every rank: all see the same m) while the peers still map the
+    // old one: it is retired, not freed, until every rank has dropped its mapping -- map_peers closes them before its
+    // first collective, so once that collective has completed here nobody maps the old buffer any more.
+    void* retired = nullptr;
+    if (m * 32 > had && cm.peer_state == 1 && cm.peer_bytes != 0) {
+        HODOR_CUDA_TRY(cudaDeviceSynchronize());  // this rank's own step B of the previous call still reads it
+        retired = cm.buf[1];
+        cm.buf[1] = nullptr;
+        cm.buf_bytes[1] = 0;
+    }
+    struct Retire {
+        void* p;
+        ~Retire() {
+            if (p) cudaFree(p);
+        }
+    } retire{retired};
     int rc = cm.ensure(0, m * 32);
     if (!rc) rc = cm.ensure(1, m * 32);
     if (rc) return rc;
     // multi-pass local transforms only: the single-block kernel (m <= 2^11) has no peer-store path
     const bool want_peers = log_n - cm.log_g >= 12;
-    if (want_peers && (cm.peer_state == 0 || (cm.peer_state == 1 && cm.buf_bytes[1] != had))) {
+    if (retired != nullptr || (want_peers && (cm.peer_state == 0 || (cm.peer_state == 1 && cm.buf_bytes[1] != had)))) {
         rc = map_peers(cm, cm.buf_bytes[1], st);
         if (rc) return rc;
     }
