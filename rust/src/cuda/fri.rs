@@ -3,8 +3,8 @@
 //! `proof_from_lde` is `NaiveFriIop::proof_from_lde_by_values` (src/fri/fri_on_values.rs:11-159) as
 //! one call: l0 tree, then per layer fold -> tree -> root -> challenge, final iNTT, all enqueued on
 //! one CUDA stream with no host round trip; the prototype stays in HBM behind a handle.
-//! `prototype_into_proof` is `produce_proof` (src/fri/query_producer.rs:10-53) with `iop.query(..)`
-//! replaced by `hodor_cuda_fri_query`.  `verify_proof` is the reference's CPU verifier, unchanged.
+//! `prototype_into_proof` is `produce_proof` (src/fri/query_producer.rs:10-53) as one call,
+//! `hodor_cuda_fri_produce_proof` (all openings gathered on the device, one copy).  `verify_proof` is the reference's CPU verifier, unchanged.
 use std::marker::PhantomData;
 
 use crate::domains::Domain;
@@ -65,7 +65,8 @@ impl<F: CudaField> CudaFriPrototype<F> {
         (nodes, values)
     }
 
-    fn query(&self, layer: usize, natural_index: usize, size: usize) -> TrivialBlake2sIopQuery<F> {
+    /// One opening of one layer (`iop.query(idx, values)` of the reference).
+    pub fn query(&self, layer: usize, natural_index: usize, size: usize) -> TrivialBlake2sIopQuery<F> {
         let depth = size.trailing_zeros() as usize;
         let mut value = F::zero();
         let mut path = vec![[0u8; 32]; depth];
@@ -77,22 +78,33 @@ impl<F: CudaField> CudaFriPrototype<F> {
         TrivialBlake2sIopQuery::from_parts(natural_index, value, path)
     }
 
+    /// `FRIProofPrototype::produce_proof` (src/fri/query_producer.rs:10-53) in ONE library call: for every
+    /// committed layer the two members of the coset of the running index (sorted as
+    /// `TrivialCombiner::get_coset_for_natural_index` does, src/iop/trivial_coset_combiner.rs:31-43), their
+    /// values and authentication paths, gathered on the device and copied out once.
     pub fn produce_proof(self, natural_first_element_index: usize) -> Result<FRIProof<F, CudaBlake2sIOP<F>>, SynthesisError> {
-        let mut domain_size = self.initial_degree_plus_one * self.lde_factor;
-        let mut domain_idx = natural_first_element_index;
-        let mut queries = vec![];
-        for layer in 0..self.roots.len() {
-            let coset = <TrivialCombiner<F> as CosetCombiner<F>>::get_coset_for_natural_index(domain_idx, domain_size);
-            if coset.len() != <TrivialCombiner<F> as CosetCombiner<F>>::COSET_SIZE {
-                return Err(SynthesisError::InvalidValue(format!("invalid coset size, expected {}, got {}",
-                                                                <TrivialCombiner<F> as CosetCombiner<F>>::COSET_SIZE, coset.len())));
+        let layers = self.roots.len();
+        let domain_size = self.initial_degree_plus_one * self.lde_factor;
+        assert!(natural_first_element_index < domain_size); // query(): assert!(natural_index < self.size())
+        let depth0 = domain_size.trailing_zeros() as usize;
+        let total: usize = (0..layers).map(|l| 2 * (depth0 - l)).sum();
+        let mut indices = vec![0u64; 2 * layers];
+        let mut values = vec![F::zero(); 2 * layers];
+        let mut paths = vec![[0u8; 32]; total];
+        let got = ffi::check(unsafe {
+            ffi::hodor_cuda_fri_produce_proof(self.handle, natural_first_element_index as u64, indices.as_mut_ptr(),
+                                              ffi::as_u64_mut(&mut values), paths.as_mut_ptr() as *mut u8)
+        })?;
+        assert!(got as usize == total);
+        let mut queries = Vec::with_capacity(2 * layers);
+        let mut off = 0;
+        for layer in 0..layers {
+            let depth = depth0 - layer;
+            for q in 0..2 {
+                let i = 2 * layer + q;
+                queries.push(TrivialBlake2sIopQuery::from_parts(indices[i] as usize, values[i], paths[off..off + depth].to_vec()));
+                off += depth;
             }
-            for idx in coset.into_iter() {
-                queries.push(self.query(layer, idx, domain_size));
-            }
-            let (next_idx, next_size) = Domain::<F>::index_and_size_for_next_domain(domain_idx, domain_size);
-            domain_idx = next_idx;
-            domain_size = next_size;
         }
         Ok(FRIProof::<F, CudaBlake2sIOP<F>> {
             queries,

@@ -180,6 +180,24 @@ impl<F: CudaField> CommittedOracle<F> {
         out
     }
 
+    /// Several openings in one launch and one pair of copies (the query phase of `Prover::prove` opens every
+    /// register oracle at the same indices, src/prover/mod.rs:142-151).
+    pub fn query_batch(&self, natural_indices: &[usize]) -> Vec<TrivialBlake2sIopQuery<F>> {
+        let depth = self.size.trailing_zeros() as usize;
+        let idx: Vec<u64> = natural_indices.iter().map(|&i| i as u64).collect();
+        assert!(idx.iter().all(|&i| i < self.size));
+        let mut values = vec![F::zero(); idx.len()];
+        let mut paths = vec![[0u8; 32]; idx.len() * depth];
+        let rc = unsafe {
+            ffi::hodor_cuda_tree_query_batch(self.handle, idx.as_ptr(), idx.len() as u32, ffi::as_u64_mut(&mut values),
+                                             paths.as_mut_ptr() as *mut u8)
+        };
+        assert!(rc == depth as i32, "hodor_cuda_tree_query_batch failed: {}", ffi::last_error());
+        natural_indices.iter().enumerate()
+            .map(|(k, &i)| TrivialBlake2sIopQuery::from_parts(i, values[k], paths[k * depth..(k + 1) * depth].to_vec()))
+            .collect()
+    }
+
     /// Device pointer of the values: input of `hodor_cuda_fri_commit(.., lde_on_device = 1, ..)`.
     pub fn device_values(&self) -> *const u64 {
         unsafe { ffi::hodor_cuda_tree_values(self.handle) as *const u64 }

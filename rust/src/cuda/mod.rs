@@ -5,7 +5,8 @@
 //!   * oracle       -- `CudaBlake2sIOP<F>: IOP<F>` in `iop.rs` (tree built on the GPU, `nodes` in the
 //!                     reference's heap layout) and `CommittedOracle<F>` (values + tree stay in HBM);
 //!   * FRI          -- `CudaFriIop<F>: FriIop<F>` in `fri.rs` (whole commit chain on the device);
-//!   * setup        -- `PrecomputedOmegas` and the ALI inverse divisors of `Prover::new` in `ali.rs`.
+//!   * setup        -- `PrecomputedOmegas` and the ALI inverse divisors of `Prover::new` in `ali.rs`;
+//!   * several GPUs -- `Comm`, the four-step NTT and the sharded LDE + FRI chain in `sharded.rs` (one process per GPU).
 //!
 //! `Prover<F, T, I, P, PR, FRI, A>` (src/prover/mod.rs:29) takes `I` and `FRI` as type parameters, so
 //!
@@ -21,7 +22,9 @@ pub mod ffi;
 pub mod fri;
 pub mod iop;
 pub mod poly;
+pub mod sharded;
 
 pub use self::ffi::CudaField;
 pub use self::fri::{CudaFriIop, CudaFriPrototype};
 pub use self::iop::{CommittedOracle, CudaBlake2sIOP, CudaBlake2sIopTree};
+pub use self::sharded::{Comm, DeviceVec, ShardedFriCommitment};

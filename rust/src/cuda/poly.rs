@@ -90,3 +90,75 @@ pub fn cuda_evaluate_at<F: CudaField>(poly: &Polynomial<F, Coefficients>, _worke
     assert!(rc == ffi::OK, "hodor_cuda_evaluate_at failed: {}", ffi::last_error());
     out
 }
+
+// ---- elementwise methods (src/polynomials/mod.rs:59-83, 640-683, 744-771, 817-887) ---------------------
+// op codes of include/hodor_b200.h (HODOR_OP_*)
+pub const OP_MUL: i32 = 0;
+pub const OP_ADD: i32 = 1;
+pub const OP_SUB: i32 = 2;
+pub const OP_SCALE: i32 = 3;
+pub const OP_ADD_SCALED: i32 = 4;
+pub const OP_ADD_CONST: i32 = 5;
+pub const OP_NEGATE: i32 = 6;
+pub const OP_SQUARE: i32 = 7;
+pub const OP_POW: i32 = 8;
+
+fn poly_op<F: CudaField>(op: i32, a: &mut [F], b: Option<&[F]>, scalar: Option<&F>, exp: u64) {
+    ffi::init();
+    // `other` may be shorter than `self` in the reference's add / sub (:640-652): only the common prefix is touched
+    let n = b.map(|b| if op == OP_SCALE { a.len() } else { b.len() }).unwrap_or(a.len());
+    assert!(a.len() >= n);
+    let rc = unsafe {
+        ffi::hodor_cuda_poly_op(
+            op,
+            ffi::as_u64(a),
+            b.map(|b| ffi::as_u64(b)).unwrap_or(std::ptr::null()),
+            scalar.map(|s| ffi::elem(s)).unwrap_or(std::ptr::null()),
+            exp,
+            ffi::as_u64_mut(a),
+            n as u64,
+            F::FIELD_ID,
+        )
+    };
+    assert!(rc == ffi::OK, "hodor_cuda_poly_op({}) failed: {}", op, ffi::last_error());
+}
+
+/// `add_assign` (:640-652 / :817-829), `sub_assign` (:671-683 / :860-872), `mul_assign` (:874-887).
+pub fn cuda_add_assign<F: CudaField, P: PolynomialForm>(a: &mut Polynomial<F, P>, _worker: &Worker, other: &Polynomial<F, P>) {
+    poly_op(OP_ADD, a.as_mut(), Some(other.as_ref()), None, 0)
+}
+pub fn cuda_sub_assign<F: CudaField, P: PolynomialForm>(a: &mut Polynomial<F, P>, _worker: &Worker, other: &Polynomial<F, P>) {
+    poly_op(OP_SUB, a.as_mut(), Some(other.as_ref()), None, 0)
+}
+pub fn cuda_mul_assign<F: CudaField>(a: &mut Polynomial<F, Values>, _worker: &Worker, other: &Polynomial<F, Values>) {
+    assert!(a.size() == other.size());
+    poly_op(OP_MUL, a.as_mut(), Some(other.as_ref()), None, 0)
+}
+/// `scale` (:59-70): every element times `g`.
+pub fn cuda_scale<F: CudaField, P: PolynomialForm>(a: &mut Polynomial<F, P>, _worker: &Worker, g: F) {
+    if g == F::one() {
+        return;
+    }
+    poly_op(OP_SCALE, a.as_mut(), Some(std::slice::from_ref(&g)), None, 0)
+}
+/// `negate` (:72-83).
+pub fn cuda_negate<F: CudaField, P: PolynomialForm>(a: &mut Polynomial<F, P>, _worker: &Worker) {
+    poly_op(OP_NEGATE, a.as_mut(), None, None, 0)
+}
+/// `add_assign_scaled` (:654-669 / :843-858): a += other * scaling.
+pub fn cuda_add_assign_scaled<F: CudaField, P: PolynomialForm>(a: &mut Polynomial<F, P>, _worker: &Worker, other: &Polynomial<F, P>, scaling: &F) {
+    poly_op(OP_ADD_SCALED, a.as_mut(), Some(other.as_ref()), Some(scaling), 0)
+}
+/// `add_constant` (:831-841), `square` (:760-771), `pow` (:744-758) of `Polynomial<F, Values>`.
+pub fn cuda_add_constant<F: CudaField>(a: &mut Polynomial<F, Values>, _worker: &Worker, constant: &F) {
+    poly_op(OP_ADD_CONST, a.as_mut(), None, Some(constant), 0)
+}
+pub fn cuda_square<F: CudaField>(a: &mut Polynomial<F, Values>, _worker: &Worker) {
+    poly_op(OP_SQUARE, a.as_mut(), None, None, 0)
+}
+pub fn cuda_pow<F: CudaField>(a: &mut Polynomial<F, Values>, _worker: &Worker, exp: u64) {
+    if exp == 2 {
+        return cuda_square(a, _worker);
+    }
+    poly_op(OP_POW, a.as_mut(), None, None, exp)
+}
