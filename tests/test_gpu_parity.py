@@ -897,6 +897,26 @@ def test_sharded_c_abi_two_gpus_under_torchrun():
     assert p.returncode == 0 and len(lines) == 4 and all(l["ok"] for l in lines), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
 
 
+def test_sharded_ntt_receive_buffer_regrows_under_torchrun():
+    """Sizes in an order that makes the receive buffer of the fused exchange grow twice and then be reused for
+    smaller transforms: every growth retires the old buffer until all peers have dropped their CUDA IPC mapping
+    of it and re-maps the new one (sharded.cu).  2 GPUs; skipped on a one-GPU box."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(root, "tools", "sharded_check.py")]
+    env = dict(os.environ, HODOR_CHECK_NTT_SIZES="14,18,22,20,12,22")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root, env=env)
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and len(lines) == 6 and all(l["ok"] for l in lines), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+
+
 def test_misaligned_device_pointer_is_rejected(hodor, oracle):
     """Element arrays are read with 256-bit loads: a device pointer that is not 32-byte aligned is an argument
     error, not a misaligned-address fault that would kill the context."""

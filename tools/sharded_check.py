@@ -200,6 +200,8 @@ def main():
         if os.environ.get("HODOR_CHECK_PHASES_LDE"):  # "24,4"
             a, b = (int(x) for x in os.environ["HODOR_CHECK_PHASES_LDE"].split(","))
             results.append(lde_fri_phases(a, b))
+    elif os.environ.get("HODOR_CHECK_NTT_SIZES"):  # e.g. "14,18,22,20": the receive buffer grows (re-mapped by the peers) and shrinks
+        results = [check_ntt(int(ln)) for ln in os.environ["HODOR_CHECK_NTT_SIZES"].split(",") if ln]
     else:
         results = [check_ntt(ntt_log_n), check_ntt(16), check_lde_fri(log_n, log_f), check_lde_fri(14, 4)]
     ok = all(r["ok"] for r in results)
