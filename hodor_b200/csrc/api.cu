@@ -376,6 +376,7 @@ int hodor_cuda_init(int device) {
         c->stage_threads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
     }
     if (const char* e = getenv("HODOR_FUSE_FOLD_COMMIT")) c->fuse_fold_commit = atoi(e) != 0;
+    if (const char* e = getenv("HODOR_FUSE_LAST_COMMIT")) c->fuse_last_commit = atoi(e) != 0;
     if (const char* mb = getenv("HODOR_POOL_CACHE_MB")) c->pool_cache_cap = (size_t)strtoull(mb, nullptr, 10) << 20;
     g_ctx = c.release();
     return HODOR_OK;
@@ -1226,9 +1227,26 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
             HODOR_CUDA_TRY(cudaStreamWaitEvent(c->stream, in_done[b], 0));
             src = (const uint4*)in_buf[b];
         }
+        // fused build: the last pass of the transform hashes the bottom three levels of the tree (ntt_commit.cuh)
+        c->fuse_commit.nodes = c->fuse_last_commit && total >= ((size_t)1 << 13) ? t->nodes : nullptr;
+        c->fuse_commit.done = false;
         int r = do_lde(*c, ops, src, (uint4*)t->values, log_n, log_factor, coset, c->stream);
+        const bool fused = c->fuse_commit.done;
+        c->fuse_commit.nodes = nullptr;
+        c->fuse_commit.done = false;
         if (r) return r;
         if (!coeffs_on_device) HODOR_CUDA_TRY(cudaEventRecord(comp_done[i % nbuf], c->stream));
+        if (fused) {  // levels total/2 .. total/8 are written: the rest of the tree, root and challenge
+            size_t w = 0;
+            r = merkle_upper_levels(*c, t->nodes, total >> 3, &w, c->stream);
+            if (!r) r = ops->merkle_tail(*c, t->nodes, t->nodes, (uint32_t)w, false, t->root, t->chal, c->stream);
+            if (r) return r;
+            if (roots) {
+                uint8_t* dst = roots_pinned ? c->pinned_small + 32 * (size_t)i : roots + 32 * (size_t)i;
+                HODOR_CUDA_TRY(cudaMemcpyAsync(dst, t->root, 32, cudaMemcpyDeviceToHost, c->stream));
+            }
+            return HODOR_OK;
+        }
         // the tree: beside the next polynomial's transform when there is one (see Ctx::commit_stream)
         cudaStream_t ts = c->stream;
         if (overlap) {

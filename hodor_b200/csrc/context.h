@@ -131,6 +131,15 @@ struct Ctx {
     std::set<const void*> configured_kernels;
     std::map<uint64_t, Fe> inv_cache;  // (field, log_n) -> omega_N^-1 of the FRI domain
 
+    // lift-and-commit: the last pass of the transform also hashes the bottom three tree levels of its output
+    // (ntt_commit.cuh).  hodor_cuda_lde_commit_batch sets `nodes` around the transform; Ops::ntt sets `done` when it
+    // took the fused kernel (multi-pass plan, last digit <= 8, no output scaling), else the tree is built as usual.
+    bool fuse_last_commit = false;  // HODOR_FUSE_LAST_COMMIT=1
+    struct FuseCommit {
+        uint4* nodes = nullptr;
+        bool done = false;
+    } fuse_commit;
+
     bool fuse_fold_commit = false;  // FRI chain: fold + bottom of the next tree in one kernel (HODOR_FUSE_FOLD_COMMIT=1; measured slower, profiles/r02_experiments.md)
 
     // step A of the sharded NTT: the last pass stores into the peers' receive buffers (ntt.cuh NttPass::peer)

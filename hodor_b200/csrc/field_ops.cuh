@@ -8,6 +8,7 @@
 #include "fri.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "ntt_commit.cuh"
 #include "polyops.cuh"
 
 namespace hodor {
@@ -353,6 +354,25 @@ struct Ops {
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;
     }
+    // last pass + bottom three levels of the tree over its output (ntt_commit.cuh)
+    template <int B>
+    static int launch_last_commit(Ctx& c, const NttPass& p, uint4* nodes, dim3 grid, cudaStream_t st) {
+        auto kern = ntt_last_commit_kernel<F, B>;
+        constexpr size_t smem = (size_t)256 << B;
+        if (!c.configured_kernels.count((const void*)kern)) {
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                cudaSharedmemCarveoutMaxShared));
+            c.configured_kernels.insert((const void*)kern);
+        }
+        {
+            ProfScope ps(c, st, "ntt_pass_last_commit");
+            kern<<<grid, PassOccupancy<B>::THREADS, smem, st>>>(p, nodes, c.key);
+        }
+        HODOR_CUDA_TRY(cudaGetLastError());
+        return HODOR_OK;
+    }
+
     template <bool SCALE_IN, bool LAST>
     static int launch_pass_b(Ctx& c, int b, const NttPass& p, dim3 grid, cudaStream_t st) {
         switch (b) {
@@ -567,7 +587,16 @@ struct Ops {
                 p.mid1 = plan.passes >= 4 ? plan.b[2] : 0;
                 if (plan.passes == 3) p.mid1 = 0;
                 dim3 grid((unsigned)(((size_t)L << log_n) >> (b + 3)), 1);
-                rc = launch_pass_b<false, true>(c, b, p, grid, st);
+                if (c.fuse_commit.nodes != nullptr && flags == 0 && !p.peer_on && b >= 6 && b <= 8) {
+                    switch (b) {
+                        case 6: rc = launch_last_commit<6>(c, p, c.fuse_commit.nodes, grid, st); break;
+                        case 7: rc = launch_last_commit<7>(c, p, c.fuse_commit.nodes, grid, st); break;
+                        default: rc = launch_last_commit<8>(c, p, c.fuse_commit.nodes, grid, st); break;
+                    }
+                    c.fuse_commit.done = (rc == HODOR_OK);
+                } else {
+                    rc = launch_pass_b<false, true>(c, b, p, grid, st);
+                }
             }
             if (rc) return rc;
         }

@@ -917,6 +917,23 @@ def test_sharded_ntt_receive_buffer_regrows_under_torchrun():
     assert p.returncode == 0 and len(lines) == 6 and all(l["ok"] for l in lines), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
 
 
+def test_fused_last_pass_commit_matches_oracle():
+    """HODOR_FUSE_LAST_COMMIT=1 (read at init, hence a process of its own): lift-and-commit with the bottom three
+    tree levels hashed inside the last pass of the transform (csrc/ntt_commit.cuh) gives the oracle's values and
+    nodes for every last-pass width, blowup 1..16, three fields -- and the fused kernel is the one that ran."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HODOR_FUSE_LAST_COMMIT="1")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fused_commit_check.py")], capture_output=True, text=True,
+                       timeout=900, cwd=root, env=env)
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and lines and lines[-1]["ok"] and lines[-1]["want_fused"], (p.returncode, p.stdout[-3000:], p.stderr[-2000:])
+    assert all(l["ok"] and l["fused"] for l in lines[:-1])
+
+
 def test_misaligned_device_pointer_is_rejected(hodor, oracle):
     """Element arrays are read with 256-bit loads: a device pointer that is not 32-byte aligned is an argument
     error, not a misaligned-address fault that would kill the context."""

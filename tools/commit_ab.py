@@ -1,7 +1,8 @@
 """Same-session A/B of lift-and-commit (hodor_cuda_lde_commit_batch, 2^24 x 8, 8 polynomials per call, pinned host
 coefficients): ms per polynomial.  Variants through the library's environment switches, one process each:
     HODOR_CONCURRENT_COMMIT=0 python tools/commit_ab.py   # tree of polynomial i after its LDE, on one stream
-    python tools/commit_ab.py                             # tree of polynomial i beside the LDE of polynomial i+1"""
+    python tools/commit_ab.py                             # tree of polynomial i beside the LDE of polynomial i+1
+    HODOR_FUSE_LAST_COMMIT=1 python tools/commit_ab.py    # bottom three tree levels hashed inside the last pass (ntt_commit.cuh)"""
 import ctypes as C
 import json
 import os
@@ -42,7 +43,13 @@ for _ in range(reps):
     r = chunk()
 ms = (time.perf_counter() - t0) * 1e3 / (reps * count)
 assert all(r[i].tobytes() == r0[0].tobytes() for i in range(count))
+_ffi.check(lib.hodor_cuda_profile_begin())  # per-kernel times of one more chunk (events around every launch)
+chunk()
+buf = C.create_string_buffer(1 << 16)
+_ffi.check(lib.hodor_cuda_profile_end(buf, len(buf)))
+kernels = {k["name"]: round(k["total_ms"] / count, 4) for k in json.loads(buf.value.decode())}
 print(json.dumps({"bench": "lde_commit_batch 2^24 x 8", "concurrent_commit": os.environ.get("HODOR_CONCURRENT_COMMIT", "1"),
+                  "fuse_last_commit": os.environ.get("HODOR_FUSE_LAST_COMMIT", "0"), "kernel_ms_per_polynomial": kernels,
                   "commit_priority": os.environ.get("HODOR_COMMIT_PRIORITY", "low"),
                   "backfill_persist": os.environ.get("HODOR_BACKFILL_PERSIST", "0"),
                   "backfill_block": os.environ.get("HODOR_BACKFILL_BLOCK", "128"),
