@@ -1,5 +1,5 @@
 """Small driver for ncu captures: a few passes of each hot kernel at the benchmark sizes.
-    ncu ... python tools/profile_target.py [lde|merkle|fri|ntt]"""
+    ncu ... python tools/profile_target.py [lde|merkle|fri|ntt|commit]"""
 import os
 import sys
 
@@ -30,6 +30,13 @@ elif what == "merkle":
     d_nodes = dev.empty_elems(n)
     for _ in range(reps):
         dev.merkle_build(d_a, n, d_nodes, 0)
+elif what == "commit":  # lift-and-commit of one polynomial; HODOR_FUSE_LAST_COMMIT=1 -> ntt_last_commit_kernel
+    import ctypes as C
+    from hodor_b200 import _ffi
+    for _ in range(reps):
+        ins, outs = (C.c_void_p * 1)(d_a.data_ptr()), (C.c_void_p * 1)()
+        _ffi.check(_ffi.lib.hodor_cuda_lde_commit_batch(ins, 1, 24, 3, 1, 1, outs, None, 0))
+        _ffi.lib.hodor_cuda_tree_free(outs[0])
 elif what == "fri":
     for _ in range(reps):
         p = dev.fri_commit(d_a, 8, 1, 0)
