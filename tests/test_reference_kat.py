@@ -175,7 +175,7 @@ def test_find_c_constants_on_the_gpu(hodor):
         _ffi.check(_ffi.lib.hodor_cuda_elementwise(op, _p(a), _p(b), _p(out), C.c_uint64(a.shape[0]), STARK))
         return out
 
-    def inv(a):
+    def batch_inv(a):
         a = np.ascontiguousarray(a).copy()
         _ffi.check(_ffi.lib.hodor_cuda_batch_inversion(_p(a), C.c_uint64(a.shape[0]), STARK))
         return a
@@ -184,7 +184,7 @@ def test_find_c_constants_on_the_gpu(hodor):
         mul = staticmethod(lambda a, b: ew(0, a, b))
         add = staticmethod(lambda a, b: ew(1, a, b))
         sub = staticmethod(lambda a, b: ew(2, a, b))
-        inv = staticmethod(inv)
+        inv = staticmethod(batch_inv)
 
     one = fld.one(STARK)
     c, e, f = find_c(Ops, one, lanes=lanes)
