@@ -13,7 +13,9 @@
  * output of the reference's own `find_c` test: ~3000 dependent Montgomery mul / add / sub and
  * one inversion over `experiments::Fr`, reproduced bit for bit by fe_mul / fe_add / fe_sub /
  * fe_inv below (tests/test_reference_kat.py).  That pins row a1 (field arithmetic); the
- * transforms, the tree and the FRI chain built on it stay unpinned.
+ * transforms, the tree and the FRI chain built on it stay unpinned against the reference,
+ * but are held to independent third-party code: sympy's ntt / intt for serial_fft, best_fft,
+ * ifft and the (coset) LDE (tests/test_third_party_pins.py), hashlib for Blake2s.
  * The un-vendored dependencies whose published algorithms are
  * restated here:  ff_ce "0.7" (derive(PrimeField): 4 x u64 little-endian limbs, Montgomery
  * R = 2^256, canonical representatives, ROOT_OF_UNITY = GENERATOR^((p-1)/2^S));
