@@ -31,6 +31,8 @@ CASES = [(0, 12, 8, True),         # 6+6
          (0, 17, 4, True),         # 9+8 (digits below 6 are not built)
          (0, 18, 8, True),         # 6+6+6
          (0, 20, 8, True)]         # 7+7+6, expanded tables
+max_log = int(os.environ.get("FUSED_CHECK_MAX_LOG", "99"))  # compute-sanitizer runs: keep the small shapes only
+CASES = [c for c in CASES if c[1] <= max_log]
 ok_all = True
 for fid, log_n, L, coset in CASES:
     a = O.random_elements(fid, 1 << log_n, seed=7000 + 31 * log_n + L)
