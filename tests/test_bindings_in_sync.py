@@ -111,3 +111,66 @@ def test_python_ctypes_table_matches_the_header():
         assert len(args) == len(params), (name, len(args), len(params))
         for a, p in zip(args, params):
             assert a in CTYPES_OF_C[c_param_type(p)], (name, p, a)
+
+
+def _rust_sources():
+    d = os.path.join(ROOT, "rust", "src")
+    for dirpath, _, files in os.walk(d):
+        for f in sorted(files):
+            if f.endswith(".rs"):
+                yield os.path.join(dirpath, f)
+
+
+def _strip_rust_comments_and_strings(s: str) -> str:
+    s = re.sub(r"//[^\n]*", "", s)
+    s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
+    s = re.sub(r'"(?:[^"\\]|\\.)*"', '""', s, flags=re.S)  # `\` + newline continues a string literal
+    s = re.sub(r"'(?:[^'\\]|\\.)'", "' '", s)  # char literals ('S'), not lifetimes
+    return s
+
+
+def test_rust_files_are_lexically_balanced():
+    """No compiler here: at least every bracket of every committed .rs file closes."""
+    pairs = {")": "(", "]": "[", "}": "{"}
+    for path in _rust_sources():
+        stack = []
+        for ch in _strip_rust_comments_and_strings(open(path).read()):
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in pairs:
+                assert stack and stack.pop() == pairs[ch], path
+        assert not stack, path
+
+
+def test_rust_calls_of_the_c_abi_have_the_declared_arity():
+    """Every `hodor_*(..)` call in the shim passes as many arguments as ffi.rs (== the header) declares."""
+    declared = {name: len(params) for name, (_, params) in rust_prototypes().items()}
+    seen = set()
+    for path in _rust_sources():
+        if path.endswith("ffi.rs"):
+            text = _strip_rust_comments_and_strings(open(path).read())
+            text = text[:text.index('extern "" {')] + text[text.index("\n}\n", text.index('extern "" {')):]  # skip the declarations
+        else:
+            text = _strip_rust_comments_and_strings(open(path).read())
+        for m in re.finditer(r"\b(hodor_\w+)\s*\(", text):
+            name, i, depth, commas, any_arg = m.group(1), m.end(), 1, 0, False
+            while depth:
+                ch = text[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    commas += 1
+                if depth >= 1 and not ch.isspace():
+                    any_arg = True
+                i += 1
+            args = text[m.end():i - 1]
+            if args.rstrip().endswith(","):
+                commas -= 1  # trailing comma of a multi-line call
+            n = commas + 1 if any_arg else 0
+            assert name in declared, (path, name)
+            assert n == declared[name], (path, name, n, declared[name])
+            seen.add(name)
+    assert {"hodor_cuda_lde_fri_sharded", "hodor_cuda_ntt_sharded", "hodor_cuda_fri_produce_proof", "hodor_cuda_poly_op",
+            "hodor_cuda_lde_commit", "hodor_cuda_merkle_build"} <= seen
