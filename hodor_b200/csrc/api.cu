@@ -376,7 +376,7 @@ int hodor_cuda_init(int device) {
         c->stage_threads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
     }
     if (const char* e = getenv("HODOR_FUSE_FOLD_COMMIT")) c->fuse_fold_commit = atoi(e) != 0;
-    if (const char* e = getenv("HODOR_FUSE_LAST_COMMIT")) c->fuse_last_commit = atoi(e) != 0;
+    if (const char* e = getenv("HODOR_FUSE_LAST_COMMIT")) c->fuse_last_commit = atoi(e);
     if (const char* mb = getenv("HODOR_POOL_CACHE_MB")) c->pool_cache_cap = (size_t)strtoull(mb, nullptr, 10) << 20;
     g_ctx = c.release();
     return HODOR_OK;
@@ -1228,7 +1228,7 @@ int hodor_cuda_lde_commit_batch(const uint64_t* const* coeffs, uint32_t count, u
             src = (const uint4*)in_buf[b];
         }
         // fused build: the last pass of the transform hashes the bottom three levels of the tree (ntt_commit.cuh)
-        c->fuse_commit.nodes = c->fuse_last_commit && total >= ((size_t)1 << 13) ? t->nodes : nullptr;
+        c->fuse_commit.nodes = c->fuse_last_commit > 0 && total >= ((size_t)1 << 13) ? t->nodes : nullptr;
         c->fuse_commit.done = false;
         int r = do_lde(*c, ops, src, (uint4*)t->values, log_n, log_factor, coset, c->stream);
         const bool fused = c->fuse_commit.done;

@@ -100,7 +100,10 @@ struct Ctx {
     size_t full_budget = (size_t)24 << 30;  // HODOR_TABLE_BUDGET_MB overrides; 0 disables
 
     // freed prototype / tree / staging blocks kept for reuse (a committed 2^27 oracle is 8 GiB); HODOR_POOL_CACHE_MB
-    size_t pool_cache_cap = (size_t)64 << 30;
+    // 96 GiB: the eight committed 2^27 oracles of one lift-and-commit batch (8 GiB each) fit, so a prover cycling through
+    // them makes no driver allocation calls (with 64 GiB one block was released and re-allocated per batch: 0.7-2 ms per
+    // polynomial, erratic).  The cache is dropped and the allocation retried when the driver runs out of memory.
+    size_t pool_cache_cap = (size_t)96 << 30;
     std::vector<std::pair<void*, size_t>> pool_free_list;
     std::map<void*, size_t> pool_live;
     void* pool_alloc(size_t bytes);
@@ -134,7 +137,7 @@ struct Ctx {
     // lift-and-commit: the last pass of the transform also hashes the bottom three tree levels of its output
     // (ntt_commit.cuh).  hodor_cuda_lde_commit_batch sets `nodes` around the transform; Ops::ntt sets `done` when it
     // took the fused kernel (multi-pass plan, last digit <= 8, no output scaling), else the tree is built as usual.
-    bool fuse_last_commit = false;  // HODOR_FUSE_LAST_COMMIT=1
+    int fuse_last_commit = 1;  // HODOR_FUSE_LAST_COMMIT: 0 off, 1 last digits 7 and 8 (24 resident warps per SM), 2 also 6 (16 warps)
     struct FuseCommit {
         uint4* nodes = nullptr;
         bool done = false;

@@ -16,7 +16,10 @@
 // merkle.cuh on them: 8 leaf + 7 node compressions, node levels nL/2, nL/4, nL/8 written.  The rest of the tree
 // (merkle_upper_levels + tail) is enqueued by the host as for the unfused build.
 //
-// Off by default until measured faster: HODOR_FUSE_LAST_COMMIT=1 (read at hodor_cuda_init).
+// Measured (profiles/r02_experiments.md): 16.66 ms against 6.70 + 10.80 ms for the two separate kernels at 2^24 x 8, 0.5 ms
+// (1.3-1.8 %) per lift-and-commit in every configuration.  HODOR_FUSE_LAST_COMMIT (read at hodor_cuda_init): 1, the default,
+// takes this kernel for last digits 7 and 8 (24 resident warps per SM, as the leaf kernel has); 2 also for 6 (64-thread
+// blocks, 16 warps: fewer than the hashing wants); 0 never.
 #pragma once
 #include "merkle.cuh"
 #include "ntt.cuh"

@@ -18,7 +18,8 @@ from hodor_b200 import _ffi
 
 H.init(0)
 lib = _ffi.lib
-n, count = 1 << 24, 8
+log_n = int(os.environ.get("COMMIT_AB_LOG_N", "24"))
+n, count = 1 << log_n, 8
 rng = np.random.default_rng(1)
 a = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
 a[:, 3] = rng.integers(0, 0x73EDA753299D7D48, size=n, dtype=np.uint64)
@@ -39,7 +40,7 @@ def chunk():
     outs = (C.c_void_p * count)()
     roots = np.zeros((count, 32), np.uint8)
     t = time.perf_counter()
-    _ffi.check(lib.hodor_cuda_lde_commit_batch(ins, count, 24, 3, 1, int(on_device), outs, roots.ctypes.data_as(_ffi.u8p), 0))
+    _ffi.check(lib.hodor_cuda_lde_commit_batch(ins, count, log_n, 3, 1, int(on_device), outs, roots.ctypes.data_as(_ffi.u8p), 0))
     call_s += time.perf_counter() - t
     for i in range(count):
         lib.hodor_cuda_tree_free(outs[i])
@@ -49,7 +50,7 @@ def chunk():
 r0 = chunk()
 call_s = 0.0
 t0 = time.perf_counter()
-reps = 3 if count > 1 else 12
+reps = (3 if count > 1 else 12) * (1 if log_n >= 24 else 4)
 for _ in range(reps):
     r = chunk()
 ms = (time.perf_counter() - t0) * 1e3 / (reps * count)
@@ -60,8 +61,8 @@ chunk()
 buf = C.create_string_buffer(1 << 16)
 _ffi.check(lib.hodor_cuda_profile_end(buf, len(buf)))
 kernels = {k["name"]: round(k["total_ms"] / count, 4) for k in json.loads(buf.value.decode())}
-print(json.dumps({"bench": "lde_commit_batch 2^24 x 8", "concurrent_commit": os.environ.get("HODOR_CONCURRENT_COMMIT", "1"),
-                  "fuse_last_commit": os.environ.get("HODOR_FUSE_LAST_COMMIT", "0"), "kernel_ms_per_polynomial": kernels,
+print(json.dumps({"bench": f"lde_commit_batch 2^{log_n} x 8", "concurrent_commit": os.environ.get("HODOR_CONCURRENT_COMMIT", "1"),
+                  "fuse_last_commit": os.environ.get("HODOR_FUSE_LAST_COMMIT", "1 (default)"), "kernel_ms_per_polynomial": kernels,
                   "commit_priority": os.environ.get("HODOR_COMMIT_PRIORITY", "low"),
                   "backfill_persist": os.environ.get("HODOR_BACKFILL_PERSIST", "0"),
                   "backfill_block": os.environ.get("HODOR_BACKFILL_BLOCK", "128"),

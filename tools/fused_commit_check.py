@@ -1,9 +1,9 @@
 """Parity of lift-and-commit with the tree's bottom three levels hashed inside the last pass of the transform
 (hodor_b200/csrc/ntt_commit.cuh) against the CPU oracle: values and every node, over every last-pass width
 (6, 7, 8), two- to four-pass plans, blowups 1 .. 16, plain and coset, three fields.
-    HODOR_FUSE_LAST_COMMIT=1 python tools/fused_commit_check.py
-Prints one JSON line per case and a summary; exit code 1 on any mismatch, or if the fused kernel was not the one
-that ran (the switch is read at hodor_cuda_init)."""
+    HODOR_FUSE_LAST_COMMIT=2 python tools/fused_commit_check.py      # 0: never fused, 1 (default): last digits 7 and 8, 2: also 6
+Prints one JSON line per case and a summary; exit code 1 on any mismatch, or if a case did not run the kernel its
+plan and the level call for (the switch is read at hodor_cuda_init)."""
 import ctypes as C
 import json
 import os
@@ -17,7 +17,18 @@ from hodor_b200 import _ffi
 from oracle import oracle as O  # the checker
 
 H.init(0)
-want_fused = os.environ.get("HODOR_FUSE_LAST_COMMIT", "0") not in ("", "0")
+level = int(os.environ.get("HODOR_FUSE_LAST_COMMIT", "1") or "1")  # 0 off, 1 (default) last digits 7 and 8, 2 also 6
+
+
+def last_digit(log_n, max_digit=8):
+    """context.h make_plan: digits balanced in 6..max_digit, most significant first."""
+    passes = -(-log_n // max_digit)
+    if log_n // passes < 6 and passes > 2:
+        passes -= 1
+    base, rem = divmod(log_n, passes)
+    return base + (1 if passes - 1 < rem else 0)
+
+
 #        field, log_n, L, coset      plan (digits, last one is the fused kernel's width)
 CASES = [(0, 12, 8, True),         # 6+6
          (0, 13, 1, False),        # 7+6, plain NTT commit: 8 adjacent outputs as the columns
@@ -44,13 +55,15 @@ for fid, log_n, L, coset in CASES:
     lde = O.lde(fid, a, log_n, L, coset) if L > 1 else (O.fft(fid, a, log_n, coset=coset))
     nodes = O.merkle_create(fid, lde)
     fused = "ntt_pass_last_commit" in kernels
+    want_fused = (6 if level >= 2 else 7) <= last_digit(log_n) <= 8 and level > 0
     ok = bool(np.array_equal(orc.values(), lde) and np.array_equal(orc.nodes, nodes) and orc.get_root() == nodes[1].tobytes())
     ok = ok and fused == want_fused and ("merkle_levels_leaf" in kernels) != fused
     q = orc.query((1 << log_n) * L - 3)
     ok = ok and H.TrivialBlake2sIOP.verify_query(q, orc.get_root())
     orc.free()
     ok_all = ok_all and ok
-    print(json.dumps({"field": fid, "log_n": log_n, "lde_factor": L, "coset": coset, "fused": fused, "ok": ok,
+    print(json.dumps({"field": fid, "log_n": log_n, "lde_factor": L, "coset": coset, "last_digit": last_digit(log_n), "fused": fused, "ok": ok,
                       "kernels": kernels}), flush=True)
-print(json.dumps({"check": "fused last pass + commit == oracle", "want_fused": want_fused, "cases": len(CASES), "ok": ok_all}))
+print(json.dumps({"check": "lift-and-commit == oracle, last pass fused with the tree's bottom levels as the level says", "level": level,
+                  "cases": len(CASES), "ok": ok_all}))
 sys.exit(0 if ok_all else 1)
