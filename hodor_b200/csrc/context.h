@@ -137,7 +137,10 @@ struct Ctx {
     // lift-and-commit: the last pass of the transform also hashes the bottom three tree levels of its output
     // (ntt_commit.cuh).  hodor_cuda_lde_commit_batch sets `nodes` around the transform; Ops::ntt sets `done` when it
     // took the fused kernel (multi-pass plan, last digit <= 8, no output scaling), else the tree is built as usual.
-    int fuse_last_commit = 1;  // HODOR_FUSE_LAST_COMMIT: 0 off, 1 last digits 7 and 8 (24 resident warps per SM), 2 also 6 (16 warps)
+    // HODOR_FUSE_LAST_COMMIT: 0 off; 1 (default) plans whose last digit is 8 -- measured 36.63 against 37.12 ms per
+    // lift-and-commit of a 2^24 x 8 polynomial; 2 also 7 and 3 also 6: measured slower than the separate tree, which
+    // runs beside the next polynomial's transform (2^22 x 8: 8.97 against 8.73 ms, 2^20 x 8: 2.20 against 2.10 ms)
+    int fuse_last_commit = 1;
     struct FuseCommit {
         uint4* nodes = nullptr;
         bool done = false;

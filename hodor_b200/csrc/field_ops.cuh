@@ -587,7 +587,7 @@ struct Ops {
                 p.mid1 = plan.passes >= 4 ? plan.b[2] : 0;
                 if (plan.passes == 3) p.mid1 = 0;
                 dim3 grid((unsigned)(((size_t)L << log_n) >> (b + 3)), 1);
-                if (c.fuse_commit.nodes != nullptr && flags == 0 && !p.peer_on && b >= (c.fuse_last_commit >= 2 ? 6 : 7) && b <= 8) {
+                if (c.fuse_commit.nodes != nullptr && flags == 0 && !p.peer_on && c.fuse_last_commit > 0 && b >= 9 - c.fuse_last_commit && b <= 8) {
                     switch (b) {
                         case 6: rc = launch_last_commit<6>(c, p, c.fuse_commit.nodes, grid, st); break;
                         case 7: rc = launch_last_commit<7>(c, p, c.fuse_commit.nodes, grid, st); break;

@@ -17,9 +17,10 @@
 // (merkle_upper_levels + tail) is enqueued by the host as for the unfused build.
 //
 // Measured (profiles/r02_experiments.md): 16.66 ms against 6.70 + 10.80 ms for the two separate kernels at 2^24 x 8, 0.5 ms
-// (1.3-1.8 %) per lift-and-commit in every configuration.  HODOR_FUSE_LAST_COMMIT (read at hodor_cuda_init): 1, the default,
-// takes this kernel for last digits 7 and 8 (24 resident warps per SM, as the leaf kernel has); 2 also for 6 (64-thread
-// blocks, 16 warps: fewer than the hashing wants); 0 never.
+// (1.3-1.8 %) per lift-and-commit of that shape in every configuration; for plans that end in a 7- or 6-bit digit
+// (128- / 64-thread blocks) the fused kernel is no faster than its two parts and loses against the separate tree, which
+// runs beside the next polynomial's transform.  HODOR_FUSE_LAST_COMMIT (read at hodor_cuda_init): 1, the default,
+// takes this kernel when the last digit is 8; 2 also for 7; 3 also for 6; 0 never.
 #pragma once
 #include "merkle.cuh"
 #include "ntt.cuh"

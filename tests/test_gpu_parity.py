@@ -917,11 +917,11 @@ def test_sharded_ntt_receive_buffer_regrows_under_torchrun():
     assert p.returncode == 0 and len(lines) == 6 and all(l["ok"] for l in lines), (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
 
 
-@pytest.mark.parametrize("level", ["0", "1", "2"])
+@pytest.mark.parametrize("level", ["0", "1", "3"])
 def test_fused_last_pass_commit_matches_oracle(level):
     """HODOR_FUSE_LAST_COMMIT (read at init, hence a process of its own): lift-and-commit with the bottom three tree
-    levels hashed inside the last pass of the transform (csrc/ntt_commit.cuh) for no plan (0), for last digits 7 and
-    8 (1, the default) and for 6 as well (2) gives the oracle's values and nodes over every last-pass width, blowup
+    levels hashed inside the last pass of the transform (csrc/ntt_commit.cuh) for no plan (0), for plans ending in an
+    8-bit digit (1, the default) and for every plan (3) gives the oracle's values and nodes over every last-pass width, blowup
     1..16, three fields -- and each case ran the kernel its plan and the level call for."""
     import json
     import os
@@ -935,7 +935,7 @@ def test_fused_last_pass_commit_matches_oracle(level):
     assert p.returncode == 0 and lines and lines[-1]["ok"] and lines[-1]["level"] == int(level), (p.returncode, p.stdout[-3000:], p.stderr[-2000:])
     assert all(l["ok"] for l in lines[:-1])
     fused = [l["fused"] for l in lines[:-1]]
-    assert (not any(fused)) if level == "0" else (all(fused) if level == "2" else (any(fused) and not all(fused)))
+    assert (not any(fused)) if level == "0" else (all(fused) if level == "3" else (any(fused) and not all(fused)))
 
 
 def test_misaligned_device_pointer_is_rejected(hodor, oracle):

@@ -2,7 +2,7 @@
 coefficients): ms per polynomial.  Variants through the library's environment switches, one process each:
     HODOR_CONCURRENT_COMMIT=0 python tools/commit_ab.py   # tree of polynomial i after its LDE, on one stream
     python tools/commit_ab.py                             # tree of polynomial i beside the LDE of polynomial i+1
-    HODOR_FUSE_LAST_COMMIT=1 python tools/commit_ab.py    # bottom three tree levels hashed inside the last pass (ntt_commit.cuh)"""
+    HODOR_FUSE_LAST_COMMIT=0 python tools/commit_ab.py    # never hash the bottom three tree levels inside the last pass (ntt_commit.cuh; 3: always)"""
 import ctypes as C
 import json
 import os

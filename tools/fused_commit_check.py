@@ -1,7 +1,7 @@
 """Parity of lift-and-commit with the tree's bottom three levels hashed inside the last pass of the transform
 (hodor_b200/csrc/ntt_commit.cuh) against the CPU oracle: values and every node, over every last-pass width
 (6, 7, 8), two- to four-pass plans, blowups 1 .. 16, plain and coset, three fields.
-    HODOR_FUSE_LAST_COMMIT=2 python tools/fused_commit_check.py      # 0: never fused, 1 (default): last digits 7 and 8, 2: also 6
+    HODOR_FUSE_LAST_COMMIT=3 python tools/fused_commit_check.py      # 0: never fused, 1 (default): last digit 8, 2: also 7, 3: also 6
 Prints one JSON line per case and a summary; exit code 1 on any mismatch, or if a case did not run the kernel its
 plan and the level call for (the switch is read at hodor_cuda_init)."""
 import ctypes as C
@@ -17,7 +17,7 @@ from hodor_b200 import _ffi
 from oracle import oracle as O  # the checker
 
 H.init(0)
-level = int(os.environ.get("HODOR_FUSE_LAST_COMMIT", "1") or "1")  # 0 off, 1 (default) last digits 7 and 8, 2 also 6
+level = int(os.environ.get("HODOR_FUSE_LAST_COMMIT", "1") or "1")  # 0 off, 1 (default) last digit 8, 2 also 7, 3 also 6
 
 
 def last_digit(log_n, max_digit=8):
@@ -55,7 +55,7 @@ for fid, log_n, L, coset in CASES:
     lde = O.lde(fid, a, log_n, L, coset) if L > 1 else (O.fft(fid, a, log_n, coset=coset))
     nodes = O.merkle_create(fid, lde)
     fused = "ntt_pass_last_commit" in kernels
-    want_fused = (6 if level >= 2 else 7) <= last_digit(log_n) <= 8 and level > 0
+    want_fused = level > 0 and 9 - level <= last_digit(log_n) <= 8
     ok = bool(np.array_equal(orc.values(), lde) and np.array_equal(orc.nodes, nodes) and orc.get_root() == nodes[1].tobytes())
     ok = ok and fused == want_fused and ("merkle_levels_leaf" in kernels) != fused
     q = orc.query((1 << log_n) * L - 3)
