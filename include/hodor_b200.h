@@ -55,7 +55,7 @@ const char* hodor_cuda_last_error(void);
 /* the HODOR_ERR_* code that goes with hodor_cuda_last_error() (for entry points that return a handle or NULL) */
 int hodor_cuda_last_error_code(void);
 /* Handles (FRI prototypes, committed oracles) and staging buffers are carved from a cache of device blocks that
- * is kept across calls ($HODOR_POOL_CACHE_MB, default 64 GiB, oldest blocks released first); this hands every
+ * is kept across calls ($HODOR_POOL_CACHE_MB, default 96 GiB, oldest blocks released first); this hands every
  * cached block that is not in use back to the driver. */
 int hodor_cuda_trim(void);
 /* bytes of device workspace + cached twiddle tables currently held */
