@@ -229,6 +229,70 @@ def test_plan_covers_all_sizes():
             assert sum(digits) == ln and all(6 <= d <= 9 for d in digits) and passes <= 4, (md, ln, digits)
 
 
+def _plan(ln, md=8):
+    passes = (ln + md - 1) // md
+    if ln // passes < 6 and passes > 2:
+        passes -= 1
+    base, rem = divmod(ln, passes)
+    return [base + (1 if i < rem else 0) for i in range(passes)]
+
+
+def _groups(b):
+    """csrc/ntt.cuh Groups<B>: widths of the register-resident butterfly groups of a 2^B tile."""
+    if b in (7, 8):
+        r = [1 if b == 7 else 2, 2, 2]
+    else:
+        rem = b - 3
+        r2 = rem if rem <= 3 else (rem + 1) // 2
+        r = [3, r2, rem - r2]
+    r.append(b - sum(r))
+    return r
+
+
+def _local_out_index(b, pos):
+    """csrc/ntt.cuh local_out_index<B>: tile position (digits k1 | k2 | k3 | k4, MSB first) -> local output index."""
+    r1, r2, r3, r4 = _groups(b)
+    k1 = pos >> (r2 + r3 + r4)
+    k2 = (pos >> (r3 + r4)) & ((1 << r2) - 1)
+    k3 = (pos >> r4) & ((1 << r3) - 1)
+    k4 = pos & ((1 << r4) - 1)
+    return k1 | (k2 << r1) | (k3 << (r1 + r2)) | (k4 << (r1 + r2 + r3))
+
+
+def test_last_pass_tile_columns_are_aligned_runs_of_eight_outputs():
+    """Index map of the last pass (csrc/ntt.cuh store_global, csrc/ntt_commit.cuh out_index), restated.  What the fused
+    last pass + commit kernel relies on: for every plan and every blowup the 8 columns of one tile position are 8
+    ADJACENT, 8-ALIGNED outputs of the interleaved natural-order vector -- one complete 2^3 subtree of leaves -- and
+    over all blocks every output is produced exactly once."""
+    for ln, log_l in [(12, 0), (12, 1), (12, 2), (12, 3), (13, 4), (14, 3), (15, 0), (16, 3), (17, 2), (18, 3), (18, 1), (25, 0)]:  # the last one: four passes (7+6+6+6), two middle digits
+        digits = _plan(ln)
+        b, b1 = digits[-1], digits[0]
+        mid0 = digits[1] if len(digits) >= 3 else 0
+        mid1 = digits[2] if len(digits) >= 4 else 0
+        li = min(log_l, 3)
+        m = ln - b - b1
+        blocks = (1 << (ln + log_l)) >> (b + 3)
+        seen = np.zeros(1 << (ln + log_l), np.uint8)
+        for block in range(blocks):
+            t = block
+            mid = t & ((1 << m) - 1)
+            t >>= m
+            k1_hi = t & ((1 << (b1 - (3 - li))) - 1)
+            coset_hi = t >> (b1 - (3 - li))
+            midrev = ((mid >> mid1) | ((mid & ((1 << mid1) - 1)) << mid0)) if mid1 else mid
+            # vectorised over the tile: positions x columns
+            pos = np.arange(1 << b)
+            kloc = np.array([_local_out_index(b, int(x)) for x in pos], np.int64) if block == 0 else kloc  # noqa: F821
+            c = np.arange(8)
+            i = (coset_hi << li) | (c & ((1 << li) - 1))
+            k1 = (k1_hi << (3 - li)) | (c >> li)
+            k = k1[None, :] | (midrev << b1) | (kloc[:, None] << (ln - b))
+            out = i[None, :] + (k << log_l)
+            assert np.all(out[:, 0] % 8 == 0) and np.all(out == out[:, :1] + c[None, :]), (ln, log_l, block)
+            seen[out.ravel()] += 1
+        assert np.all(seen == 1), (ln, log_l, digits)
+
+
 @pytest.mark.parametrize("fid", FIELDS, ids=FIELD_IDS)
 def test_fri_verify_proof_on_oracle_built_proofs(oracle, fid):
     """NaiveFriIop.verify_proof (src/fri/verifier.rs:130-290, host-side scalar work through the
