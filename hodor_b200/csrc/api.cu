@@ -1497,7 +1497,7 @@ hodor_fri_proto* fri_commit_impl(Ctx* c, const uint64_t* lde, uint64_t n, uint32
     const uint32_t log_n0 = log2u(n);
     for (int i = 0; i < steps && !rc; i++) {
         const size_t m = n >> i;
-        if (c->fuse_fold_commit && m / 2 > merkle_tail_width() && m / 2 >= 16) {
+        if (c->fuse_fold_commit && m / 2 > merkle_tail_width() && m / 2 >= 2048) {  // the fused kernel works on tiles of 2048 outputs
             // fold + the bottom three levels of the new tree in one kernel, the rest of the tree as usual
             rc = ops->fri_fold_commit(*c, p->values[i], m, log_n0, (uint32_t)i, p->chal + 2 * i, p->values[i + 1], p->nodes[i + 1], st);
             size_t w = 0;

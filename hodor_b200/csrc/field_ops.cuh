@@ -816,19 +816,23 @@ struct Ops {
         const uint4* flat = nullptr;
         int rc = fri_tables(c, log_n0, &t, &flat, st);
         if (rc) return rc;
-        const size_t half = n / 2, groups = half >> 3;
-        if (half < 16) return fail(HODOR_ERR_INVALID_ARG, "internal: fold_commit needs at least 16 outputs");
-        const unsigned block = groups >= 148 * 256 ? 256 : (groups >= 148 * 64 ? 128 : 32);
-        size_t g = (groups + block - 1) / block;
-        if (g > 148 * 16) g = 148 * 16;
+        const size_t half = n / 2;
+        if (half < FOLD_COMMIT_TILE || half % FOLD_COMMIT_TILE) return fail(HODOR_ERR_INVALID_ARG, "internal: fold_commit needs a multiple of 2048 outputs");
+        const unsigned g = (unsigned)(half / FOLD_COMMIT_TILE);
+        constexpr size_t smem = (size_t)FOLD_COMMIT_TILE * sizeof(Fe);
+        const void* kern = flat ? (const void*)fri_fold_commit_kernel<F, true> : (const void*)fri_fold_commit_kernel<F, false>;
+        if (!c.configured_kernels.count(kern)) {
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HODOR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            c.configured_kernels.insert(kern);
+        }
         {
             ProfScope ps(c, st, "fri_fold_commit");
             if (flat)
-                fri_fold_commit_kernel<F, true><<<(unsigned)g, block, 0, st>>>(in, out, nodes, half, t->two_level(), flat, layer, chal,
-                                                                               c.key, 0u);
+                fri_fold_commit_kernel<F, true><<<g, 256, smem, st>>>(in, out, nodes, half, t->two_level(), flat, layer, chal, c.key, 0u);
             else
-                fri_fold_commit_kernel<F, false><<<(unsigned)g, block, 0, st>>>(in, out, nodes, half, t->two_level(), nullptr, layer,
-                                                                                chal, c.key, 0u);
+                fri_fold_commit_kernel<F, false><<<g, 256, smem, st>>>(in, out, nodes, half, t->two_level(), nullptr, layer, chal, c.key,
+                                                                       0u);
         }
         HODOR_CUDA_TRY(cudaGetLastError());
         return HODOR_OK;

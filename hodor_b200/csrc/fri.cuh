@@ -52,45 +52,59 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* in, uint4* o
 }
 
 // One layer fused with the bottom three levels of its Merkle tree (src/fri/fri_on_values.rs:61-119: fold, then
-// I::create(next_values)).  A thread owns 8 consecutive outputs: it folds them one by one, stores each value,
-// hashes it while it is still in registers and combines the hashes as a thread-serial 2^3 subtree, writing the
-// node levels half/2, half/4, half/8 of the new tree.  The layer's values are therefore read by no hashing
-// kernel (32 * half bytes of HBM reads and one launch per layer saved) and the fold's multiplier work (2
-// fixed-operand multiplies per leaf) issues between the ALU-bound compressions of other warps.
-#ifndef HODOR_FOLD_COMMIT_MINBLOCKS
-#define HODOR_FOLD_COMMIT_MINBLOCKS 1  // 3: cap the kernel at 85 registers (A/B build, profiles/r02_experiments.md)
-#endif
+// I::create(next_values)), second design.  The first one (a thread folded its own 8 consecutive outputs inside the
+// hashing recursion: 128 registers, 256-byte strided loads) was slower than the separate kernels
+// (profiles/r02_experiments.md).  Here a block folds 2048 consecutive outputs with the plain kernel's coalesced
+// accesses -- thread t takes outputs t, t + 256, ... --, stores them to HBM and to a 64 KiB shared tile, and after one
+// barrier thread t hashes outputs 8t .. 8t + 7 from the tile as a thread-serial 2^3 subtree (merkle.cuh), writing the
+// node levels half/2, half/4, half/8: the structure of the fused last pass of the transform (ntt_commit.cuh), at its
+// residency (3 blocks of 256 threads per SM, <= 85 registers).  The layer's values are read by no hashing kernel, and
+// the fold's multiplier work issues beside the ALU-bound compressions of the other resident blocks.
+// half must be a multiple of 2048.
+constexpr uint32_t FOLD_COMMIT_TILE = 2048;
 template <class F, bool FLAT>
-__global__ void __launch_bounds__(256, HODOR_FOLD_COMMIT_MINBLOCKS) fri_fold_commit_kernel(const uint4* in, uint4* out, uint4* nodes, size_t half, TwoLevel winv,
+__global__ void __launch_bounds__(256, 3) fri_fold_commit_kernel(const uint4* in, uint4* out, uint4* nodes, size_t half, TwoLevel winv,
                                                               const uint4* winv_flat, uint32_t layer, const uint4* challenge,
                                                               const __grid_constant__ B2sState key, uint32_t zero) {
-    const Field<F> fld(threadIdx.x & zero);
-    const Fe c = ld_fe(challenge, 0);
-    FePre cp;
-    if constexpr (FLAT) fld.make_pre(c, cp.w, cp.q);
-    const size_t groups = half >> 3;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
-        auto leaf = [&](size_t idx) -> Digest {
+    extern __shared__ uint4 tile[];  // element e of the block's 2048 outputs at tile[2e], tile[2e + 1]
+    const uint32_t tid = threadIdx.x;
+    const Field<F> fld(tid & zero);
+    const size_t base = (size_t)blockIdx.x * FOLD_COMMIT_TILE;
+    {
+        const Fe c = ld_fe(challenge, 0);
+        FePre cp;
+        if constexpr (FLAT) fld.make_pre(c, cp.w, cp.q);
+#pragma unroll 1
+        for (uint32_t j = 0; j < FOLD_COMMIT_TILE / 256; j++) {
+            const uint32_t e = j * 256 + tid;
+            const size_t idx = base + e;
             const Fe f0 = ld_fe(in, idx), f1 = ld_fe(in, idx + half);
             const Fe even = fld.add(f0, f1);
             Fe odd = fld.sub(f0, f1);
-            const uint64_t e = (uint64_t)idx << layer;
+            const uint64_t ex = (uint64_t)idx << layer;
             if constexpr (FLAT) {
-                odd = mul_by(fld, odd, ld_pre(winv_flat, (size_t)e));
+                odd = mul_by(fld, odd, ld_pre(winv_flat, (size_t)ex));
                 odd = mul_by(fld, odd, cp);
             } else {
-                odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, e));
+                odd = fld.mul(odd, two_level_pow(fld, winv, 0, 0, ex));
                 odd = fld.mul(odd, c);
             }
             const Fe v = fld.halve(fld.add(odd, even));
             st_fe(out, idx, v);
-            Digest d;
-#pragma unroll
-            for (int i = 0; i < 8; i++) d.w[i] = v.v[i];
-            return tree_hash_leaf(key, d);
-        };
-        merkle_subtree_fn<3>(key, nodes, half, g << 3, leaf);
+            sts_elem(tile, e, v);
+        }
     }
+    __syncthreads();
+    const size_t first = base + 8 * (size_t)tid;
+    auto leaf = [&](size_t idx) -> Digest {
+        const uint32_t e = (uint32_t)(idx - base);
+        const uint4 a = tile[2 * e], b = tile[2 * e + 1];
+        Digest d;
+        d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
+        d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+        return tree_hash_leaf(key, d);
+    };
+    merkle_subtree_fn<3>(key, nodes, half, first, leaf);
 }
 
 }  // namespace hodor

@@ -938,6 +938,24 @@ def test_fused_last_pass_commit_matches_oracle(level):
     assert (not any(fused)) if level == "0" else (all(fused) if level == "3" else (any(fused) and not all(fused)))
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_fri_chain_fold_commit_switch_matches_oracle(fused):
+    """HODOR_FUSE_FOLD_COMMIT (read at init, hence a process of its own): the FRI commit chain with the fold fused with
+    the bottom three levels of the next tree (csrc/fri.cuh fri_fold_commit_kernel) and with separate kernels gives
+    the oracle's roots, challenges, final coefficients, layer values and nodes -- and the kernel the switch names ran."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HODOR_FUSE_FOLD_COMMIT=fused)
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fri_fused_check.py")], capture_output=True, text=True,
+                       timeout=900, cwd=root, env=env)
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and lines and lines[-1]["ok"] and lines[-1]["want_fused"] == (fused == "1"), (p.returncode, p.stdout[-3000:], p.stderr[-2000:])
+    assert all(l["ok"] and l["fused"] == (fused == "1") for l in lines[:-1])
+
+
 def test_misaligned_device_pointer_is_rejected(hodor, oracle):
     """Element arrays are read with 256-bit loads: a device pointer that is not 32-byte aligned is an argument
     error, not a misaligned-address fault that would kill the context."""

@@ -1,7 +1,7 @@
 """Same-session A/B of the FRI commit chain on 2^24 values (blowup 8): prints ms per chain and the per-kernel
 profile.  Variants are selected through the library's environment switches, one process each:
     HODOR_FUSE_FOLD_COMMIT=0 python tools/fri_ab.py      # fold and leaf hashing as separate kernels
-    python tools/fri_ab.py                               # fused fold + bottom of the tree (default)"""
+    HODOR_FUSE_FOLD_COMMIT=1 python tools/fri_ab.py      # fold fused with the bottom three levels of the next tree"""
 import ctypes as C
 import json
 import os
@@ -37,5 +37,5 @@ dev.fri_commit(d, L, 1, 0).free()
 buf = C.create_string_buffer(1 << 16)
 _ffi.check(_ffi.lib.hodor_cuda_profile_end(buf, len(buf)))
 prof = {r["name"]: {"launches": r["count"], "total_ms": round(r["total_ms"], 4)} for r in json.loads(buf.value.decode())}
-print(json.dumps({"bench": "fri_chain", "log_n": log_n, "lde_factor": L, "fuse_fold_commit": os.environ.get("HODOR_FUSE_FOLD_COMMIT", "1"),
+print(json.dumps({"bench": "fri_chain", "log_n": log_n, "lde_factor": L, "fuse_fold_commit": os.environ.get("HODOR_FUSE_FOLD_COMMIT", "default"),
                   "tail_max": os.environ.get("HODOR_MERKLE_TAIL_MAX", "default"), "ms_per_chain": ms, "kernels": prof}))
