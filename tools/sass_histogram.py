@@ -18,7 +18,8 @@ KERNELS = [
     ("ntt_pass_kernel<BlsFr, 8, !SCALE_IN, LAST>  (last pass: natural-order / interleaved / peer stores)", "ntt_pass_kernelINS_5BlsFrELi8ELb0ELb1"),
     ("merkle_levels_kernel<3, LEAF>", "merkle_levels_kernelILi3ELb1"),
     ("fri_fold_kernel<BlsFr, FLAT>", "fri_fold_kernelINS_5BlsFrELb1"),
-    ("fri_fold_commit_kernel<BlsFr, FLAT> (fused fold + leaf subtree; off by default)", "fri_fold_commit_kernelINS_5BlsFrELb1"),
+    ("fri_fold_commit_kernel<BlsFr, FLAT> (fold into a shared tile + leaf subtrees from it; off by default)", "fri_fold_commit_kernelINS_5BlsFrELb1"),
+    ("ntt_last_commit_kernel<BlsFr, 8> (last pass + bottom three tree levels: what lift-and-commit runs at 2^24)", "ntt_last_commit_kernelINS_5BlsFrELi8"),
 ]
 PIPE = {"fma (multiplier) pipe": ("IMAD.WIDE", "IMAD.HI", "IMAD.X", "IMAD.IADD", "IMAD.MOV", "IMAD.SHL", "IMAD", "HFMA2", "FFMA"),
         "alu pipe": ("IADD3", "LOP3", "SHF", "SEL", "PRMT", "MOV", "ISETP", "LEA", "VIADD", "IABS", "FMNMX"),
