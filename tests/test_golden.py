@@ -1,5 +1,6 @@
 """Committed known-answer vectors (tests/golden/vectors.json, made by tests/golden/make_golden.py from
-the big-integer model): the C oracle must reproduce them on the CPU, the CUDA path on the GPU."""
+the big-integer model): the C oracle must reproduce them on the CPU, the CUDA path on the GPU -- and sympy's
+number-theoretic transform, an implementation from outside this repository, the NTT and LDE ones."""
 import hashlib
 import json
 import os
@@ -109,6 +110,46 @@ def check_case(impl, O, c):
 @pytest.mark.parametrize("c", CASES, ids=case_id)
 def test_oracle_reproduces_golden(oracle, c):
     check_case(OracleImpl(oracle), oracle, c)
+
+
+class SympyImpl:
+    """An implementation that shares nothing with this repository: sympy's number-theoretic transform over the prime,
+    with sympy's own choice of primitive root (the smallest one = the generator the reference declares for the two
+    fields it defines, see tests/test_third_party_pins.py).  Montgomery form in and out, as the fixtures hold it."""
+
+    GENERATOR = {0: 7, 2: 3}
+
+    def __init__(self, O):
+        self.O = O
+
+    def _io(self, fid):
+        p = self.O.limbs_to_int(self.O.field_constants(fid)["p"])
+        rinv = pow(1 << 256, -1, p)
+        to_plain = lambda a: [self.O.limbs_to_int(x) * rinv % p for x in a]  # noqa: E731
+        to_mont = lambda xs: np.stack([self.O.int_to_limbs((int(x) << 256) % p) for x in xs])  # noqa: E731
+        return p, to_plain, to_mont
+
+    def ntt(self, fid, a, ln):
+        from sympy.discrete.transforms import ntt
+        p, to_plain, to_mont = self._io(fid)
+        return to_mont(ntt(to_plain(a), p))
+
+    def lde(self, fid, a, ln, L, coset):
+        from sympy.discrete.transforms import ntt
+        p, to_plain, to_mont = self._io(fid)
+        g = self.GENERATOR[fid] if coset else 1
+        scaled = [x * pow(g, j, p) % p for j, x in enumerate(to_plain(a))]
+        return to_mont(ntt(scaled + [0] * ((L - 1) << ln), p))
+
+
+THIRD_PARTY_CASES = [c for c in CASES if c["kind"] in ("ntt", "lde") and c["field"] in SympyImpl.GENERATOR and c["log_n"] >= 1]
+
+
+@pytest.mark.parametrize("c", THIRD_PARTY_CASES, ids=case_id)
+def test_sympy_reproduces_golden_transforms(oracle, c):
+    """The committed NTT / LDE fixtures of the two fields the reference declares, from code written by someone else."""
+    pytest.importorskip("sympy")
+    check_case(SympyImpl(oracle), oracle, c)
 
 
 @pytest.mark.gpu
