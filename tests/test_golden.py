@@ -142,12 +142,74 @@ class SympyImpl:
         return to_mont(ntt(scaled + [0] * ((L - 1) << ln), p))
 
 
-THIRD_PARTY_CASES = [c for c in CASES if c["kind"] in ("ntt", "lde") and c["field"] in SympyImpl.GENERATOR and c["log_n"] >= 1]
+    # --- the FRI commit chain from its DEFINITION, not from the reference's pairing formula: interpolate the layer
+    # (sympy intt), fold the coefficients f_even + c * f_odd, evaluate on the half-size domain (sympy ntt); trees and
+    # challenges with hashlib's Blake2s (RFC 7693 keyed + personalised, src/iop/blake2s_trivial_iop.rs:8-16, :48-60).
+    @staticmethod
+    def _h(data: bytes) -> bytes:
+        return hashlib.blake2s(data, key=b"Squeamish Ossifrage", person=b"Shaftoe", digest_size=32).digest()
+
+    def _tree(self, fid, plain, p):
+        leaves = [self._h(((x << 256) % p).to_bytes(32, "little")) for x in plain]  # encode_leaf: raw Montgomery limbs
+        level = [self._h(leaves[2 * i] + leaves[2 * i + 1]) for i in range(len(leaves) // 2)]
+        while len(level) > 1:
+            level = [self._h(level[2 * i] + level[2 * i + 1]) for i in range(len(level) // 2)]
+        root = level[0]
+        capacity = self.O.field_constants(fid)["num_bits"] - 1
+        top_mask = (2**64 - 1) >> ((256 - capacity) % 64)
+        v = int.from_bytes(root, "big") & ((top_mask << 192) | (2**192 - 1))  # read_be, shave the top limb
+        return root, v
+
+    def merkle(self, fid, a):
+        """Blake2sIopTree::create's heap (src/iop/blake2s_trivial_iop.rs:131-219) with hashlib: nodes[0] zero, nodes[1]
+        the root, the level of w nodes at [w, 2w)."""
+        p, to_plain, to_mont = self._io(fid)
+        n = len(a)
+        nodes = [bytes(32)] * n
+        leaves = [self._h(np.ascontiguousarray(x).tobytes()) for x in a]
+        for i in range(n // 2):
+            nodes[n // 2 + i] = self._h(leaves[2 * i] + leaves[2 * i + 1])
+        for i in range(n // 2 - 1, 0, -1):
+            nodes[i] = self._h(nodes[2 * i] + nodes[2 * i + 1])
+        _, v = self._tree(fid, to_plain(a), p)
+        return np.frombuffer(b"".join(nodes), np.uint8).reshape(n, 32), to_mont([v])[0]
+
+    def batch_inversion(self, fid, a):
+        p, to_plain, to_mont = self._io(fid)
+        return to_mont([pow(x, -1, p) for x in to_plain(a)])
+
+    def evaluate_at(self, fid, a, z):
+        p, to_plain, to_mont = self._io(fid)
+        zz = to_plain([z])[0]
+        return to_mont([sum(x * pow(zz, j, p) for j, x in enumerate(to_plain(a))) % p])[0]
+
+    def fri(self, fid, a, L, oc):
+        from sympy.discrete.transforms import intt, ntt
+        p, to_plain, to_mont = self._io(fid)
+        values = to_plain(a)
+        steps = (len(values) // L // oc).bit_length() - 1
+        roots, challenges, layer_values = [], [], []
+        root, c = self._tree(fid, values, p)
+        roots.append(root)
+        coeffs = intt(values, p)
+        for _ in range(steps):
+            challenges.append(c)
+            coeffs = [(coeffs[2 * j] + c * coeffs[2 * j + 1]) % p for j in range(len(coeffs) // 2)]
+            values = ntt(coeffs, p)
+            layer_values.append(to_mont(values))
+            root, c = self._tree(fid, values, p)
+            roots.append(root)
+        return roots, to_mont(challenges), roots[-1], to_mont(coeffs[:oc]), layer_values
+
+
+THIRD_PARTY_CASES = [c for c in CASES if c["field"] in SympyImpl.GENERATOR and c["log_n"] >= 1]
 
 
 @pytest.mark.parametrize("c", THIRD_PARTY_CASES, ids=case_id)
-def test_sympy_reproduces_golden_transforms(oracle, c):
-    """The committed NTT / LDE fixtures of the two fields the reference declares, from code written by someone else."""
+def test_third_party_code_reproduces_golden(oracle, c):
+    """Every committed fixture of the two fields the reference declares, from code written by someone else: sympy's
+    transforms, hashlib's Blake2s, Python's modular pow (the FRI chain restated from its definition: interpolate,
+    fold the coefficients, re-evaluate -- not from the reference's pairing formula)."""
     pytest.importorskip("sympy")
     check_case(SympyImpl(oracle), oracle, c)
 
