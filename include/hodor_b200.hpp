@@ -12,6 +12,8 @@
 //   NaiveFriIop<F>, FRIProofPrototype<F>, FRIProof<F>
 //                                     src/fri/mod.rs:26-154, src/fri/fri_on_values.rs:11-159,
 //                                     src/fri/query_producer.rs:10-53
+//   Comm, DeviceVec<F>                several GPUs, one process per GPU (no counterpart in the reference: its
+//                                     parallelism is the threads of one host, src/fft/multicore.rs)
 //
 // `Result<_, SynthesisError>` becomes a thrown SynthesisError; the reference's assert!/expect panics
 // become std::logic_error.  `Worker` is accepted and ignored (the CUDA grid replaces the thread pool).
@@ -591,6 +593,104 @@ struct NaiveFriIop {  // src/fri/mod.rs:63-105
                                             size_t natural_first_element_index) {
         return prototype.produce_proof(natural_first_element_index);
     }
+};
+
+// ---- several GPUs: one process per GPU (hodor_b200.h, "several GPUs") ------------------------------------------
+// The reference's only parallelism is the threads of one host (`Worker`); its parallel_fft (src/fft/fft.rs:68-125) is
+// the four-step decomposition over CPU threads and its multi-coset LDE runs the cosets on separate threads
+// (src/polynomials/mod.rs:572-587).  Here a rank is a process that owns one GPU.  Rendezvous: rank 0 makes the id
+// (Comm::unique_id) and ships its 128 bytes to the other ranks by whatever means the host program has (MPI, a file);
+// every rank then constructs its Comm.  Same surface as rust/src/cuda/sharded.rs and hodor_b200/multigpu.py.
+
+// A vector of field elements in HBM (32 bytes per element, the reference's own in-memory form).
+template <class F>
+class DeviceVec {
+  public:
+    explicit DeviceVec(size_t len) : len_(len), ptr_(hodor_cuda_malloc((len ? len : 1) * 32), &hodor_cuda_free) {
+        if (!ptr_) check(hodor_cuda_last_error_code() < 0 ? hodor_cuda_last_error_code() : HODOR_ERR_CUDA);
+    }
+    static DeviceVec from_host(const std::vector<F>& v) {
+        DeviceVec d(v.size());
+        check(hodor_cuda_memcpy_h2d(d.ptr_.get(), v.data(), v.size() * 32, nullptr));
+        check(hodor_cuda_stream_synchronize(nullptr));
+        return d;
+    }
+    std::vector<F> to_host() const {
+        std::vector<F> v(len_);
+        check(hodor_cuda_memcpy_d2h(v.data(), ptr_.get(), len_ * 32, nullptr));
+        check(hodor_cuda_stream_synchronize(nullptr));
+        return v;
+    }
+    size_t size() const { return len_; }
+    void* data() { return ptr_.get(); }
+    const void* data() const { return ptr_.get(); }
+
+  private:
+    size_t len_;
+    std::unique_ptr<void, void (*)(void*)> ptr_;
+};
+
+// What FriProofPrototype::get_roots, .challenges and get_final_coefficients give for the unsharded chain.
+template <class F>
+struct ShardedFriCommitment {
+    std::vector<Digest> roots;
+    std::vector<F> challenges;
+    std::vector<F> final_coefficients;
+};
+
+class Comm {
+  public:
+    static std::array<uint8_t, 128> unique_id() {  // rank 0 only
+        std::array<uint8_t, 128> id{};
+        check(hodor_cuda_comm_unique_id(id.data()));
+        return id;
+    }
+    // collective; world a power of two <= 16; world == 1 needs neither NCCL nor an id
+    Comm(int rank, int world, const uint8_t* id) : rank_(rank), world_(world) { check(hodor_cuda_comm_init(rank, world, id)); }
+    ~Comm() { hodor_cuda_comm_destroy(); }
+    Comm(const Comm&) = delete;
+    Comm& operator=(const Comm&) = delete;
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+
+    // best_fft (src/fft/fft.rs:5-19) on a vector dealt over the ranks.  local: this rank's cyclic slice
+    // a[j * world + rank]; result: the rank-th (n / world^2)-element chunk of every length-(n / world) block of the
+    // natural-order output (hodor_b200.h, hodor_cuda_ntt_sharded).  Collective.
+    template <class F>
+    DeviceVec<F> ntt(const DeviceVec<F>& local, uint32_t log_n, const F& omega) const {
+        if (local.size() != (((size_t)1 << log_n) / (size_t)world_)) throw std::logic_error("ntt: wrong slice length");
+        DeviceVec<F> out(local.size());
+        check(hodor_cuda_ntt_sharded(local.data(), out.data(), log_n, omega.l, F::ID, nullptr));
+        check(hodor_cuda_stream_synchronize(nullptr));
+        return out;
+    }
+    // coset_lde (src/polynomials/mod.rs:349-352) followed by proof_from_lde_by_values (src/fri/fri_on_values.rs:11-159)
+    // with cosets, folds and the bottom of every tree sharded over the ranks; coeffs replicated.  Collective.
+    template <class F>
+    ShardedFriCommitment<F> lde_fri(const DeviceVec<F>& coeffs, uint32_t log_n, size_t factor, bool coset,
+                                    size_t output_coeffs_at_degree_plus_one) const {
+        if (!factor || (factor & (factor - 1)) || !output_coeffs_at_degree_plus_one ||
+            (output_coeffs_at_degree_plus_one & (output_coeffs_at_degree_plus_one - 1)))
+            throw std::logic_error("assert!(factor.is_power_of_two())");
+        uint32_t log_f = 0, log_o = 0;
+        while (((size_t)1 << log_f) < factor) log_f++;
+        while (((size_t)1 << log_o) < output_coeffs_at_degree_plus_one) log_o++;
+        if (log_o >= log_n) throw std::logic_error("zero folding steps (the reference panics here)");
+        const size_t steps = log_n - log_o;
+        ShardedFriCommitment<F> r;
+        r.roots.resize(steps + 1);
+        r.challenges.resize(steps);
+        r.final_coefficients.resize(output_coeffs_at_degree_plus_one);
+        const int got = check(hodor_cuda_lde_fri_sharded(coeffs.data(), log_n, log_f, coset ? 1 : 0, (uint32_t)output_coeffs_at_degree_plus_one,
+                                                         reinterpret_cast<uint8_t*>(r.roots.data()),
+                                                         reinterpret_cast<uint64_t*>(r.challenges.data()),
+                                                         reinterpret_cast<uint64_t*>(r.final_coefficients.data()), F::ID));
+        if ((size_t)got != steps) throw CudaError("lde_fri_sharded: unexpected number of folding steps");
+        return r;
+    }
+
+  private:
+    int rank_, world_;
 };
 
 }  // namespace hodor_b200

@@ -340,9 +340,31 @@ static void run_all(const char* name) {
     std::printf("%s: %s\n", name, failures == before ? "ok" : "FAILED");
 }
 
+// the multi-GPU host at world 1 (no NCCL needed): the sharded entry points must equal the single-GPU ones
+template <class F>
+static void test_comm_world1() {
+    const Worker worker;
+    Comm comm(0, 1, nullptr);
+    const uint32_t log_n = 13;
+    const auto a = random_vec<F>((size_t)1 << log_n, 4242);
+    auto poly = Polynomial<F, Coefficients>::from_coeffs(a);
+    const F omega = poly.omega;
+    const auto got = comm.ntt(DeviceVec<F>::from_host(a), log_n, omega).to_host();
+    CHECK(got == std::move(poly).fft(worker).as_ref());
+    const size_t factor = 8;
+    const auto chain = comm.lde_fri(DeviceVec<F>::from_host(a), log_n, factor, true, 1);
+    auto lde = Polynomial<F, Coefficients>::from_coeffs(a).coset_lde(worker, factor);
+    const auto proto = NaiveFriIop<F>::proof_from_lde(lde, factor, 1, worker);
+    CHECK(chain.roots == proto.get_roots());
+    CHECK(chain.challenges == proto.challenges);
+    CHECK(chain.final_coefficients == proto.final_coefficients);
+}
+
 int main() {
     try {
         init(0);
+        test_comm_world1<Bn256RsFr>();
+        test_comm_world1<Stark252Fr>();
         run_all<Bn256RsFr>("bn256.rs Fr (BLS12-381 Fr)");
         run_all<Bn254Fr>("BN254 Fr");
         run_all<Stark252Fr>("Stark252");
