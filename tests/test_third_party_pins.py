@@ -79,3 +79,48 @@ def test_gpu_transforms_match_sympy(hodor, oracle, fid):
     want = ntt(scaled + [0] * ((L - 1) << log_n), p)
     got = hodor.Polynomial.from_coeffs(fid, a).coset_lde(W, L)
     assert _plain(oracle, fid, got.as_ref()) == want
+
+
+def test_oracle_against_third_party_on_random_shapes(oracle):
+    """Random small shapes (hypothesis): sizes 1 .. 2^7, blowups 1 .. 16, plain and coset, both reference-declared
+    fields, structured and random inputs -- the oracle's LDE against sympy on the padded (and g^j-scaled) vector, and
+    its FRI commit chain against the chain restated from its definition (tests/test_golden.py SympyImpl)."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    from test_golden import SympyImpl
+
+    third = SympyImpl(oracle)
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(fid=st.sampled_from([0, 2]), log_n=st.integers(0, 7), log_l=st.integers(0, 4), coset=st.booleans(),
+           seed=st.integers(1, 2**32), shape=st.sampled_from(["random", "zero", "one", "delta", "minus_one"]))
+    def lde_case(fid, log_n, log_l, coset, seed, shape):
+        n, L = 1 << log_n, 1 << log_l
+        p = _modulus(oracle, fid)
+        a = oracle.random_elements(fid, n, seed)
+        if shape != "random":
+            plain = {"zero": [0] * n, "one": [1] * n, "delta": [1] + [0] * (n - 1), "minus_one": [p - 1] * n}[shape]
+            a = oracle.to_mont(fid, oracle.ints_to_array(plain))
+        got = oracle.lde(fid, a, log_n, L, coset) if L > 1 else oracle.fft(fid, a, log_n, coset=coset)
+        if n * L == 1:
+            assert np.array_equal(got, a)  # a transform of length one is the identity (also for the coset: g^0)
+        else:
+            assert np.array_equal(got, third.lde(fid, a, log_n, L, coset))
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(fid=st.sampled_from([0, 2]), log_n=st.integers(2, 7), log_l=st.integers(1, 3), log_o=st.integers(0, 2),
+           seed=st.integers(1, 2**32))
+    def fri_case(fid, log_n, log_l, log_o, seed):
+        n, L, oc = 1 << log_n, 1 << log_l, 1 << log_o
+        if n // L // oc < 2:
+            return  # zero folding steps: the reference panics (covered by the argument-error tests)
+        v = oracle.random_elements(fid, n, seed)
+        want = oracle.fri_commit(fid, v, L, oc)
+        roots, chal, final_root, final_coeffs, values = third.fri(fid, v, L, oc)
+        assert [bytes(r) for r in roots] == want.roots() and final_root == want.final_root
+        assert np.array_equal(chal, want.challenges) and np.array_equal(final_coeffs, want.final_coefficients)
+        assert all(np.array_equal(x, y) for x, y in zip(values, want.layer_values))
+
+    lde_case()
+    fri_case()
