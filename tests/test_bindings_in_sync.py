@@ -174,3 +174,19 @@ def test_rust_calls_of_the_c_abi_have_the_declared_arity():
             seen.add(name)
     assert {"hodor_cuda_lde_fri_sharded", "hodor_cuda_ntt_sharded", "hodor_cuda_fri_produce_proof", "hodor_cuda_poly_op",
             "hodor_cuda_lde_commit", "hodor_cuda_merkle_build"} <= seen
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md's table of environment switches == the HODOR_* variables the library, the Python mirror and
+    bench.py actually read."""
+    read = set()
+    csrc = os.path.join(ROOT, "hodor_b200", "csrc")
+    for f in os.listdir(csrc):
+        if os.path.isfile(os.path.join(csrc, f)):
+            read |= set(re.findall(r'getenv\("(HODOR_[A-Z0-9_]+)"\)', open(os.path.join(csrc, f)).read()))
+    for path in [os.path.join(ROOT, "bench.py")] + [os.path.join(ROOT, "hodor_b200", f) for f in os.listdir(os.path.join(ROOT, "hodor_b200"))
+                                                     if f.endswith(".py")]:
+        read |= set(re.findall(r'environ(?:\.get)?[\[(]\s*"(HODOR_[A-Z0-9_]+)"', open(path).read()))
+    documented = set(re.findall(r"`(HODOR_[A-Z0-9_]+)`", open(os.path.join(ROOT, "INTEGRATION.md")).read()))
+    assert read <= documented, sorted(read - documented)
+    assert documented <= read | {"HODOR_B200_LIB_DIR", "HODOR_CUDA_DEVICE"}, sorted(documented - read)  # the two are read by rust/
